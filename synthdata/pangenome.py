@@ -1,0 +1,152 @@
+"""Seeded synthetic pangenomes and reads of the shapes BASELINE.json names.
+
+Tooling for tests and bench only.  Everything is numpy (host); sizes up to ~1e9 bases are fine.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.arange(256, dtype=np.uint8)
+for a, b in zip(b"ACGTacgt", b"TGCAtgca"):
+    _COMP[a] = b
+
+SEP = 1   # document separator byte
+END = 0   # final terminator byte
+
+
+def revcomp(seq: np.ndarray) -> np.ndarray:
+    return _COMP[seq[::-1]]
+
+
+def _mutate(rng: np.random.Generator, seq: np.ndarray, snp: float, indel: float) -> np.ndarray:
+    """Independent SNPs (rate snp) and 1-3 bp indels (rate indel, half insertions) on a copy of seq."""
+    out = seq.copy()
+    if snp > 0:
+        k = rng.binomial(out.size, snp)
+        pos = rng.integers(0, out.size, k)
+        # substitute by a *different* base: rotate within ACGT by 1..3
+        code = np.searchsorted(ACGT, out[pos])
+        out[pos] = ACGT[(code + rng.integers(1, 4, k)) & 3]
+    if indel > 0:
+        k = rng.binomial(out.size, indel)
+        if k:
+            pos = np.sort(rng.integers(1, out.size - 4, k))
+            pos = pos[np.concatenate(([True], np.diff(pos) > 8))]
+            ln = rng.integers(1, 4, pos.size)
+            ins = rng.random(pos.size) < 0.5
+            pieces, prev = [], 0
+            for p, l, i in zip(pos.tolist(), ln.tolist(), ins.tolist()):
+                pieces.append(out[prev:p])
+                if i:
+                    pieces.append(ACGT[rng.integers(0, 4, l)])
+                    prev = p
+                else:
+                    prev = p + l
+            pieces.append(out[prev:])
+            out = np.concatenate(pieces)
+    return out
+
+
+def make_haplotypes(genome_len: int, n_hap: int, *, snp: float = 1e-3, indel: float = 0.0,
+                    seed: int = 1, tree: bool = False) -> list[np.ndarray]:
+    """n_hap haplotypes of one random ACGT genome.
+
+    tree=False: star phylogeny, each haplotype = base + independent variants (configs 1, 2).
+    tree=True : HPRC-like shared variants: a balanced binary tree whose every edge adds variants at
+                rate snp/depth, so variants are shared by clades (config 3).
+    """
+    rng = np.random.default_rng(seed)
+    base = ACGT[rng.integers(0, 4, genome_len)]
+    if not tree:
+        return [_mutate(rng, base, snp, indel) for _ in range(n_hap)]
+    depth = max(1, int(np.ceil(np.log2(max(2, n_hap)))))
+    level = [base]
+    for _ in range(depth):
+        nxt = []
+        for g in level:
+            nxt.append(_mutate(rng, g, snp / depth, indel / depth))
+            nxt.append(_mutate(rng, g, snp / depth, indel / depth))
+        level = nxt
+    return level[:n_hap]
+
+
+def build_text(haps: list[np.ndarray], *, with_revcomp: bool = True):
+    """Concatenate sequences with SEP between and END last (SURVEY.md section 4.3 layout).
+
+    Returns (text u8, seq_starts int64 [n_seq+1], doc_of_seq int32 [n_seq]).  With revcomp, each
+    document contributes two sequences (forward, reverse complement) as mumemto -r does.
+    """
+    seqs, doc = [], []
+    for d, h in enumerate(haps):
+        seqs.append(h)
+        doc.append(d)
+        if with_revcomp:
+            seqs.append(revcomp(h))
+            doc.append(d)
+    total = sum(s.size + 1 for s in seqs)
+    text = np.empty(total, dtype=np.uint8)
+    starts = np.zeros(len(seqs) + 1, dtype=np.int64)
+    p = 0
+    for i, s in enumerate(seqs):
+        starts[i] = p
+        text[p:p + s.size] = s
+        p += s.size
+        text[p] = SEP
+        p += 1
+    text[-1] = END
+    starts[-1] = p
+    return text, starts, np.asarray(doc, dtype=np.int32)
+
+
+def sample_reads(text: np.ndarray, seq_starts: np.ndarray, n_reads: int, read_len: int, *,
+                 sub: float = 0.01, ins: float = 0.0, dele: float = 0.0, seed: int = 2,
+                 len_jitter: float = 0.0):
+    """Reads drawn uniformly from the sequences of `text` with errors.
+
+    Returns (seqs u8 concatenated, offsets u64 [n_reads+1]).  Substitution-only reads keep exactly
+    read_len bases; with indels (nanopore-like) lengths vary.  len_jitter>0 draws the pre-error length
+    from a log-normal around read_len (long-read length spread).
+    """
+    rng = np.random.default_rng(seed)
+    n_seq = len(seq_starts) - 1
+    seq_len = np.diff(seq_starts) - 1
+    if len_jitter > 0:
+        lens = np.clip((read_len * rng.lognormal(0.0, len_jitter, n_reads)).astype(np.int64), 16, int(seq_len.min()))
+    else:
+        lens = np.full(n_reads, min(read_len, int(seq_len.min())), dtype=np.int64)
+    which = rng.integers(0, n_seq, n_reads)
+    start = seq_starts[which] + (rng.random(n_reads) * (seq_len[which] - lens + 1)).astype(np.int64)
+    if ins == 0 and dele == 0:
+        offsets = np.zeros(n_reads + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(lens)
+        total = int(offsets[-1])
+        # gather: index = start[read] + within-read offset
+        read_id = np.repeat(np.arange(n_reads, dtype=np.int64), lens)
+        within = np.arange(total, dtype=np.int64) - offsets[:-1].astype(np.int64)[read_id]
+        seqs = text[start[read_id] + within]
+        if sub > 0:
+            k = rng.binomial(total, sub)
+            pos = rng.integers(0, total, k)
+            code = np.searchsorted(ACGT, seqs[pos])
+            seqs[pos] = ACGT[(code + rng.integers(1, 4, k)) & 3]
+        return seqs, offsets
+    # indel model: per base decide keep / substitute / delete, and insert before with prob ins
+    out, offsets = [], np.zeros(n_reads + 1, dtype=np.uint64)
+    for i in range(n_reads):
+        src = text[start[i]:start[i] + lens[i]].copy()
+        u = rng.random(src.size)
+        subm = u < sub
+        code = np.searchsorted(ACGT, src[subm])
+        src[subm] = ACGT[(code + rng.integers(1, 4, int(subm.sum()))) & 3]
+        keep = ~((u >= sub) & (u < sub + dele))
+        insm = rng.random(src.size) < ins
+        reps = keep.astype(np.int64) + insm
+        rd = np.repeat(src, reps)
+        # positions that are inserted copies get a random base
+        first = np.cumsum(reps) - reps
+        ins_pos = first[insm]
+        rd[ins_pos] = ACGT[rng.integers(0, 4, ins_pos.size)]
+        out.append(rd)
+        offsets[i + 1] = offsets[i] + np.uint64(rd.size)
+    return (np.concatenate(out) if out else np.zeros(0, np.uint8)), offsets
