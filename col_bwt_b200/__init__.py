@@ -1,0 +1,249 @@
+"""col_bwt_b200 -- B200-native query path of col-bwt (PML + chain ids), Python host mirror over the C-ABI.
+
+The compute lives in `libcolbwt_b200.so` (hand-written sm_100a CUDA, see csrc/); this module is a thin ctypes
+binding whose class `ColPml` mirrors the reference's `col_pml` (include/col_bwt.hpp:386-575):
+
+    reference                                   here
+    col_pml tbl; tbl.load(ifstream)             tbl = ColPml.load(path)
+    tbl.query_pml(pattern, m) -> (pml, cid)     tbl.query_pml(pattern) -> (pml, cid)      (one read)
+    per-read loop of pml_query.cpp:74-86        tbl.query(seqs, offsets) -> (pml, cid)    (whole batch)
+    tbl.size() / runs() / bwt_runs()            tbl.n / tbl.r / tbl.bwt_r
+
+There is no CPU fallback: importing works without a GPU (so symbols can be checked), every compute call raises
+`ColBwtError` if no CUDA device is present, and a missing shared library raises at import.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcolbwt_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C col_bwt_b200/csrc`). col_bwt_b200 has no CPU fallback."
+    )
+
+_L = C.CDLL(LIB_PATH)
+
+
+class ColBwtError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        super().__init__(f"{where}: status {code}: {_L.colbwt_last_error().decode(errors='replace')}")
+
+
+class Stats(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("bwt_r", C.c_uint64), ("marked_rows", C.c_uint64),
+                ("slow_rows", C.c_uint64), ("device_bytes", C.c_uint64), ("max_row_len", C.c_uint32), ("n_devices", C.c_int32)]
+
+
+# every symbol include/colbwt_b200.h declares
+EXPORTS = {
+    "colbwt_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "colbwt_index_from_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "colbwt_index_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "colbwt_index_free": (None, [C.c_void_p]),
+    "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
+    "colbwt_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "colbwt_host_free": (None, [C.c_void_p]),
+    "colbwt_batch_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "colbwt_batch_run": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "colbwt_batch_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "colbwt_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "colbwt_batch_launches": (C.c_int, [C.c_void_p]),
+    "colbwt_batch_free": (None, [C.c_void_p]),
+    "colbwt_format_stats": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_uint64]),
+    "colbwt_gather_bench": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "colbwt_last_error": (C.c_char_p, []),
+    "colbwt_version": (C.c_char_p, []),
+}
+for _name, (_res, _args) in EXPORTS.items():
+    _f = getattr(_L, _name)   # AttributeError here = the library does not export what the header declares
+    _f.restype = _res
+    _f.argtypes = _args
+
+PML_U16, PML_U32 = 2, 4
+
+
+def version() -> str:
+    return _L.colbwt_version().decode()
+
+
+def _check(rc: int, where: str) -> None:
+    if rc != 0:
+        raise ColBwtError(rc, where)
+
+
+def _dev_array(devices):
+    if devices is None:
+        return None, 1
+    if isinstance(devices, int):
+        return None, devices
+    arr = (C.c_int * len(devices))(*devices)
+    return arr, len(devices)
+
+
+def _as_batch(seqs, offsets):
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    if offsets.ndim != 1 or offsets.size < 1:
+        raise ValueError("offsets must hold n_reads+1 entries")
+    return seqs, offsets
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from colbwt_host_alloc (freed with the object)."""
+
+    def __init__(self, n: int, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(1, n * self.dtype.itemsize)
+        self.ptr = _L.colbwt_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise ColBwtError(-6, "colbwt_host_alloc")
+        self.array = np.frombuffer((C.c_uint8 * self.nbytes).from_address(self.ptr), dtype=self.dtype, count=n)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            _L.colbwt_host_free(self.ptr)
+            self.ptr = None
+
+
+class Batch:
+    """A batch of reads resident on one GPU (colbwt_batch_*): upload once, traverse many times."""
+
+    def __init__(self, index: "ColPml", seqs, offsets, pml_width: int = PML_U16, device_slot: int = 0):
+        self.seqs, self.offsets = _as_batch(seqs, offsets)
+        self.index = index
+        self.pml_width = pml_width
+        self.n_bases = int(self.offsets[-1] - self.offsets[0])
+        h = C.c_void_p()
+        _check(_L.colbwt_batch_upload(index._h, device_slot, self.seqs.ctypes.data, self.offsets.ctypes.data,
+                                      self.offsets.size - 1, pml_width, C.byref(h)), "colbwt_batch_upload")
+        self._h = h
+
+    def run(self, iters: int = 1) -> float:
+        """Traverse `iters` times; returns CUDA-event milliseconds per traversal."""
+        ms = C.c_float()
+        _check(_L.colbwt_batch_run(self._h, iters, C.byref(ms)), "colbwt_batch_run")
+        return float(ms.value)
+
+    @property
+    def launches(self) -> int:
+        return _L.colbwt_batch_launches(self._h)
+
+    def download(self):
+        pml = np.zeros(self.n_bases, np.uint16 if self.pml_width == 2 else np.uint32)
+        cid = np.zeros(self.n_bases, np.uint8)
+        _check(_L.colbwt_batch_download(self._h, pml.ctypes.data, cid.ctypes.data), "colbwt_batch_download")
+        return pml, cid
+
+    def device_ptrs(self):
+        p, c, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(_L.colbwt_batch_device_ptrs(self._h, C.byref(p), C.byref(c), C.byref(n)), "colbwt_batch_device_ptrs")
+        return p.value, c.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.colbwt_batch_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class ColPml:
+    """Mirror of the reference's `col_pml` (include/col_bwt.hpp:386-575) with the table in GPU memory."""
+
+    def __init__(self, handle):
+        self._h = handle
+        st = Stats()
+        _check(_L.colbwt_index_stats(self._h, C.byref(st)), "colbwt_index_stats")
+        self.stats = st
+        self.n, self.r, self.bwt_r = st.n, st.r, st.bwt_r
+
+    @classmethod
+    def load(cls, path: str, devices=None) -> "ColPml":
+        """col_pml::load (col_bwt.hpp:375-380). `path` = `<prefix>.col_pml` or the prefix itself.
+        devices: None (GPU 0), an int (that many GPUs, 0..k-1) or a list of CUDA ordinals."""
+        arr, k = _dev_array(devices)
+        h = C.c_void_p()
+        _check(_L.colbwt_index_load(os.fsencode(path), arr, k, C.byref(h)), "colbwt_index_load")
+        return cls(h)
+
+    @classmethod
+    def from_rows(cls, rows: np.ndarray, bwt_r: int, n: int, devices=None) -> "ColPml":
+        """From memory: `rows` = the packed 18-byte col_thr rows as they sit in the file."""
+        raw = np.ascontiguousarray(rows).view(np.uint8).reshape(-1)
+        if raw.size % 18:
+            raise ValueError("rows must be a whole number of 18-byte records")
+        arr, k = _dev_array(devices)
+        h = C.c_void_p()
+        _check(_L.colbwt_index_from_rows(raw.ctypes.data, bwt_r, n, raw.size // 18, arr, k, C.byref(h)), "colbwt_index_from_rows")
+        return cls(h)
+
+    def size(self) -> int:          # LF_table::size
+        return self.n
+
+    def runs(self) -> int:          # LF_table::runs
+        return self.r
+
+    def bwt_runs(self) -> int:      # col_bwt::bwt_runs
+        return self.bwt_r
+
+    def query(self, seqs, offsets, pml_width: int = PML_U16, out=None):
+        """The per-read loop of pml_query.cpp:74-86 for a whole batch (host buffers in, host buffers out).
+        out = (pml_array, cid_array) to write into caller (e.g. pinned) buffers."""
+        seqs, offsets = _as_batch(seqs, offsets)
+        total = int(offsets[-1] - offsets[0])
+        if out is None:
+            pml = np.zeros(total, np.uint16 if pml_width == 2 else np.uint32)
+            cid = np.zeros(total, np.uint8)
+        else:
+            pml, cid = out
+            assert pml.dtype.itemsize == pml_width and pml.size >= total and cid.size >= total
+        _check(_L.colbwt_query(self._h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data, pml_width,
+                               cid.ctypes.data), "colbwt_query")
+        return pml, cid
+
+    def query_pml(self, pattern: bytes | str):
+        """col_pml::query_pml(pattern) (col_bwt.hpp:403-412): (PML lengths, chain ids), indexed by read position."""
+        if isinstance(pattern, str):
+            pattern = pattern.encode()
+        seq = np.frombuffer(bytes(pattern), dtype=np.uint8)
+        width = PML_U16 if seq.size < 65536 else PML_U32
+        pml, cid = self.query(seq, np.array([0, seq.size], np.uint64), width)
+        return pml.astype(np.uint64), cid.astype(np.uint64)
+
+    def batch(self, seqs, offsets, pml_width: int = PML_U16, device_slot: int = 0) -> Batch:
+        return Batch(self, seqs, offsets, pml_width, device_slot)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _L.colbwt_index_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def format_stats(read_id: str, values: np.ndarray) -> bytes:
+    """Text of pml_query.cpp:79-85 for one read."""
+    v = np.ascontiguousarray(values)
+    if v.dtype.itemsize not in (1, 2, 4):
+        v = v.astype(np.uint32)
+    rid = read_id.encode()
+    need = _L.colbwt_format_stats(None, 0, rid, len(rid), v.ctypes.data, v.dtype.itemsize, v.size)
+    buf = C.create_string_buffer(need)
+    k = _L.colbwt_format_stats(buf, need, rid, len(rid), v.ctypes.data, v.dtype.itemsize, v.size)
+    return buf.raw[:k]
+
+
+def gather_bench(bytes_: int, loads: int, dependent: bool = False, device: int = 0) -> float:
+    """Random 32-byte-sector gather rate (sectors/s) over a buffer of `bytes_` bytes."""
+    out = C.c_double()
+    _check(_L.colbwt_gather_bench(device, bytes_, loads, int(dependent), C.byref(out)), "colbwt_gather_bench")
+    return float(out.value)

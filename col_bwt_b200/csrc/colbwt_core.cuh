@@ -1,0 +1,359 @@
+// colbwt_core.cuh -- packed move-table row, row builder and the per-lane traversal state machine.
+//
+// Everything here is `__host__ __device__` so that tests/native/emulate.cpp can run the *same* logic the
+// kernels run, one lane at a time on the CPU, against the oracle (test infrastructure only: the product
+// never executes this on the host).
+//
+// Reference semantics being reproduced (paths relative to the reference tree):
+//   col_pml::_query_pml        include/col_bwt.hpp:498-529   per-base loop, CID sampled before reposition
+//   col_pml::threshold_step    include/col_bwt.hpp:531-574   successor / threshold / predecessor choice
+//   LF_table::LF               include/ds/LF_table.hpp:251-262 LF step + fast-forward
+//   LF_table::pred/succ_char   include/ds/LF_table.hpp:271-298 (replaced by precomputed per-row distances,
+//                              with an exact search over per-character row lists when they do not fit)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#else
+#define CB_HD inline
+#endif
+
+namespace colbwt {
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed row: 16 bytes, one 128-bit load.
+//   x            dest   LF destination row                                    (LF_row::interval, 32 bit)
+//   y[ 0:16)     doff   offset inside the destination row                     (LF_row::offset,   16 bit)
+//   y[16:32)     len    row length, 1..65535                                  (idx[k+1]-idx[k])
+//   meta = z | w<<32:
+//     [ 0: 8)    cid    chain id                                              (col_row::col_id)
+//     [ 8:11)    chc    0..3 = A,C,T,G ((byte>>1)&3), 4 = any other byte (exact byte in ch8[])
+//     [11:17)    mode   3 x 2 bit, slot s = (c - chc - 1) & 3 for read code c != chc:
+//                         0 jump to successor row (offset 0)          1 jump to predecessor row (offset len-1)
+//                         2 predecessor if offset < fx else successor  3 resolve by exact search (slow path)
+//     [17:47)    dist   3 x (dp:5 | ds:5<<5): distance to the predecessor / successor row of that character
+//     [47:63)    fx     the one in-row flip offset = clamp(thr[succ] - idx[k], 0, len)
+// The reference's test `pos < thr[succ]` (col_bwt.hpp:560) with pos = idx[k]+offset is offset < thr[succ]-idx[k];
+// for almost every (row, character) that is constant over the row, so two bits replace two 40-bit compares.
+// ---------------------------------------------------------------------------------------------------------
+struct Row {
+    uint32_t dest, offlen, m0, m1;
+};
+
+constexpr int CHC_OTHER = 4;
+constexpr int CODE_OTHER = 4;   // read byte present in the table but not A/C/G/T
+constexpr int CODE_ABSENT = 5;  // read byte that no row carries
+constexpr uint32_t MAX_DIST = 31;
+constexpr uint32_t MAX_ROW_LEN = 65535;
+
+CB_HD int primary_code(uint8_t c) { return (c == 'A') ? 0 : (c == 'C') ? 1 : (c == 'T') ? 2 : (c == 'G') ? 3 : -1; }
+CB_HD uint8_t primary_byte(int code) { return code == 0 ? 'A' : code == 1 ? 'C' : code == 2 ? 'T' : 'G'; }
+
+CB_HD uint32_t row_len(const Row &r) { return r.offlen >> 16; }
+CB_HD uint32_t row_doff(const Row &r) { return r.offlen & 0xFFFFu; }
+CB_HD uint32_t row_cid(const Row &r) { return r.m0 & 0xFFu; }
+CB_HD uint32_t row_chc(const Row &r) { return (r.m0 >> 8) & 7u; }
+CB_HD uint64_t row_meta(const Row &r) { return (uint64_t)r.m0 | ((uint64_t)r.m1 << 32); }
+
+// Device-resident table (all pointers in HBM).
+struct TableView {
+    const Row *rows;            // r packed rows
+    const uint8_t *ch8;         // r exact row bytes                      (slow path, "other" characters)
+    const uint64_t *idx;        // r BWT start positions                  (slow path: pos = idx[k]+offset)
+    const uint64_t *thr;        // r thresholds                           (slow path)
+    const uint32_t *char_rows;  // row numbers sorted by (byte, row)      (slow path: exact pred/succ search)
+    const uint32_t *char_start; // 257 offsets into char_rows
+    uint64_t n;
+    uint32_t r;
+    uint32_t last_len;          // len(r-1): initial offset is last_len-1 (col_bwt.hpp:503-505)
+};
+
+struct BuildView {              // inputs of build_row: unpacked reference columns
+    const uint8_t *ch8;
+    const uint64_t *idx;
+    const uint64_t *thr;
+    const uint32_t *dest;
+    const uint16_t *doff;
+    const uint8_t *cid;
+    uint64_t n;
+    uint32_t r;
+};
+
+constexpr uint32_t BUILD_FLAG_BAD_LEN = 1u;   // row of length 0 or >= 65536
+constexpr uint32_t BUILD_FLAG_SLOW = 2u;      // some (row, character) needs the exact search
+constexpr uint32_t BUILD_FLAG_BAD_LF = 4u;    // dest >= r
+
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+CB_HD Row ld_row(const Row *p)
+{
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return Row{v.x, v.y, v.z, v.w};
+}
+template <typename T> CB_HD T ld_ro(const T *p) { return __ldg(p); }
+#else
+CB_HD Row ld_row(const Row *p) { return *p; }
+template <typename T> CB_HD T ld_ro(const T *p) { return *p; }
+#endif
+
+// Build the packed row k from the reference columns.  Pure function of the columns.
+CB_HD Row build_row(const BuildView &b, uint32_t k, uint32_t *flags)
+{
+    const uint64_t i0 = b.idx[k];
+    const uint64_t i1 = (k + 1 < b.r) ? b.idx[k + 1] : b.n;
+    const uint64_t len = i1 - i0;
+    if (i1 <= i0 || len > MAX_ROW_LEN) *flags |= BUILD_FLAG_BAD_LEN;
+    if (b.dest[k] >= b.r) *flags |= BUILD_FLAG_BAD_LF;
+    const int rc = primary_code(b.ch8[k]);
+    const uint32_t chc = rc < 0 ? CHC_OTHER : (uint32_t)rc;
+    uint64_t meta = (uint64_t)b.cid[k] | ((uint64_t)chc << 8);
+    if (rc < 0) {
+        // every mismatch on this row goes through the exact search: all mode fields (and the two bits a
+        // slot-3 decode would read) are 3
+        meta |= (uint64_t)0x3F << 11;
+        meta |= (uint64_t)0x3FFFFFFF << 17;
+        *flags |= BUILD_FLAG_SLOW;
+    } else {
+        bool fx_set = false;
+        uint64_t fx = 0;
+        for (int slot = 0; slot < 3; ++slot) {
+            const uint8_t cb = primary_byte((rc + 1 + slot) & 3);
+            uint32_t dp = 0, ds = 0;
+            for (uint32_t d = 1; d <= MAX_DIST && d <= k; ++d)
+                if (b.ch8[k - d] == cb) { dp = d; break; }
+            for (uint32_t d = 1; d <= MAX_DIST && (uint64_t)k + d < b.r; ++d)
+                if (b.ch8[k + d] == cb) { ds = d; break; }
+            const bool pred_none = (dp == 0) && (k <= MAX_DIST);                        // scanned to row 0
+            const bool succ_none = (ds == 0) && ((uint64_t)k + MAX_DIST >= b.r - 1);    // scanned to row r-1
+            uint32_t mode = 3;
+            if (ds) {
+                const uint64_t t = b.thr[k + ds];
+                const uint64_t flip = (t <= i0) ? 0 : ((t - i0 >= len) ? len : t - i0);
+                if (flip == 0 || pred_none) mode = 0;            // successor whatever the offset
+                else if (dp) {
+                    if (flip >= len) mode = 1;                   // predecessor whatever the offset
+                    else if (!fx_set || fx == flip) { mode = 2; fx = flip; fx_set = true; }
+                }
+            } else if (succ_none && dp) {
+                mode = 1;                                        // no successor: thr = n, predecessor wins
+            }
+            if (mode == 3) *flags |= BUILD_FLAG_SLOW;
+            meta |= (uint64_t)mode << (11 + 2 * slot);
+            meta |= (uint64_t)(dp | (ds << 5)) << (17 + 10 * slot);
+        }
+        meta |= (fx & 0xFFFF) << 47;
+    }
+    Row r;
+    r.dest = b.dest[k];
+    r.offlen = (uint32_t)b.doff[k] | ((uint32_t)(len & 0xFFFF) << 16);
+    r.m0 = (uint32_t)meta;
+    r.m1 = (uint32_t)(meta >> 32);
+    return r;
+}
+
+// Exact restatement of threshold_step's search (col_bwt.hpp:531-574) over the sorted per-character row lists.
+// Returns false when neither a successor nor a predecessor exists (state unchanged).
+CB_HD bool slow_reposition(const TableView &t, uint32_t cur, uint32_t off, uint8_t c, uint32_t *tgt, bool *use_pred)
+{
+    uint32_t lo = ld_ro(t.char_start + c), hi = ld_ro(t.char_start + c + 1);
+    if (lo == hi) return false;
+    const uint32_t base = lo, end = hi;
+    while (lo < hi) {                                   // first list entry > cur (cur itself has another byte)
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (ld_ro(t.char_rows + mid) > cur) hi = mid; else lo = mid + 1;
+    }
+    const bool has_s = lo < end, has_p = lo > base;
+    uint64_t thr = t.n;
+    bool found = false;
+    if (has_s) {
+        const uint32_t s = ld_ro(t.char_rows + lo);
+        thr = ld_ro(t.thr + s);
+        *tgt = s;
+        *use_pred = false;
+        found = true;
+    }
+    const uint64_t pos = ld_ro(t.idx + cur) + off;
+    if (pos < thr && has_p) {
+        *tgt = ld_ro(t.char_rows + lo - 1);
+        *use_pred = true;
+        found = true;
+    }
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One batch of reads on the device.
+// ---------------------------------------------------------------------------------------------------------
+struct ReadMeta {           // 16 bytes per read
+    uint64_t out_off;       // index of base 0 of the read in pml[] / cid[]
+    uint32_t len;
+    uint32_t in_off;        // packed reads: 32-bit word index into words[]; byte reads: byte index into bytes[]
+};
+
+struct BatchView {
+    const ReadMeta *meta;   // n_packed entries, input order; reads shipped as bytes have len = 0 here
+    const ReadMeta *meta_b; // n_bytes entries: the reads that contain something outside ACGT
+    const uint32_t *words;  // 2 bit per base, 16 bases per word, base j of a read at bits 2*(j&15) of word j>>4
+    const uint8_t *bytes;   // raw bytes of the reads that contain something outside ACGT
+    void *pml;              // PmlT[total bases]
+    uint8_t *cid;           // [total bases]
+    uint32_t n_packed, n_bytes;
+};
+
+enum LaneState : uint32_t { LANE_IDLE = 0, LANE_LF = 1, LANE_REPOS_SUCC = 2, LANE_REPOS_PRED = 3 };
+
+// Per-lane registers.  Every iteration of the traversal loop performs exactly one row gather per lane
+// (`rows[addr]`) whatever the lane needs next -- LF destination, fast-forward neighbour or reposition target --
+// so no lane ever waits for another lane's extra gather, and lanes that finish a read take the next one.
+template <typename PmlT> struct Lane {
+    uint32_t state = LANE_IDLE;
+    uint32_t addr = 0;      // row to gather this iteration
+    uint32_t off = 0;       // LANE_LF: offset carried into rows[addr] (may exceed its length: fast-forward)
+    uint32_t plen = 0;      // current pseudo matching length
+    uint32_t j = 0;         // bases still to process; the next base is j-1 (right to left, col_bwt.hpp:512)
+    uint32_t in_off = 0;
+    uint32_t rw = 0;        // current packed word
+    uint64_t out_base = 0;
+    uint32_t cnt = 0;       // staged outputs
+    uint32_t accp[4] = {0, 0, 0, 0};   // 8 staged u16 PML values (lowest position in the low bits)
+    uint32_t accc[2] = {0, 0};         // 8 staged CID bytes
+};
+
+template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g)
+{
+    uint8_t *cid = bv.cid + g;
+    if (L.cnt == 8) {   // aligned full group: g % 8 == 0
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint2 *>(cid) = make_uint2(L.accc[0], L.accc[1]);
+        if (sizeof(PmlT) == 2)
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(bv.pml) + g) = make_uint4(L.accp[0], L.accp[1], L.accp[2], L.accp[3]);
+#else
+        for (int t = 0; t < 8; ++t) cid[t] = (uint8_t)(L.accc[t >> 2] >> (8 * (t & 3)));
+        if (sizeof(PmlT) == 2)
+            for (int t = 0; t < 8; ++t) reinterpret_cast<uint16_t *>(bv.pml)[g + t] = (uint16_t)(L.accp[t >> 1] >> (16 * (t & 1)));
+#endif
+    } else {
+        uint32_t c0 = L.accc[0], c1 = L.accc[1];
+        uint32_t p0 = L.accp[0], p1 = L.accp[1], p2 = L.accp[2], p3 = L.accp[3];
+        for (uint32_t t = 0; t < L.cnt; ++t) {
+            cid[t] = (uint8_t)c0;
+            c0 = (c0 >> 8) | (c1 << 24);
+            c1 >>= 8;
+            if (sizeof(PmlT) == 2) {
+                reinterpret_cast<uint16_t *>(bv.pml)[g + t] = (uint16_t)p0;
+                p0 = (p0 >> 16) | (p1 << 16);
+                p1 = (p1 >> 16) | (p2 << 16);
+                p2 = (p2 >> 16) | (p3 << 16);
+                p3 >>= 16;
+            }
+        }
+    }
+    L.cnt = 0;
+}
+
+template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)
+{
+    const uint64_t g = L.out_base + jj;
+    L.accc[1] = (L.accc[1] << 8) | (L.accc[0] >> 24);
+    L.accc[0] = (L.accc[0] << 8) | cid;
+    if (sizeof(PmlT) == 2) {
+        L.accp[3] = (L.accp[3] << 16) | (L.accp[2] >> 16);
+        L.accp[2] = (L.accp[2] << 16) | (L.accp[1] >> 16);
+        L.accp[1] = (L.accp[1] << 16) | (L.accp[0] >> 16);
+        L.accp[0] = (L.accp[0] << 16) | (plen & 0xFFFFu);
+    } else {
+        reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
+    }
+    ++L.cnt;
+    if ((g & 7) == 0 || jj == 0) lane_flush(L, bv, g);
+}
+
+// Start read `m` on this lane (zero-length reads are skipped by the caller).
+template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ReadMeta &m)
+{
+    L.state = LANE_LF;
+    L.addr = t.r - 1;               // col_bwt.hpp:504
+    L.off = t.last_len - 1;         // col_bwt.hpp:505
+    L.plen = 0;
+    L.j = m.len;
+    L.in_off = m.in_off;
+    L.out_base = m.out_off;
+    L.cnt = 0;
+    if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
+}
+
+// Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
+template <bool PACKED, typename PmlT>
+CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
+{
+    const uint32_t len = row_len(row);
+    if (L.state != LANE_LF) {
+        // rows[addr] is the reposition target (LF_table.hpp:282,297): predecessor at len-1, successor at 0
+        const uint32_t o = (L.state == LANE_REPOS_PRED) ? len - 1 : 0;
+        L.off = row_doff(row) + o;
+        L.addr = row.dest;
+        L.state = LANE_LF;
+        return;
+    }
+    if (L.off >= len && L.addr + 1 < t.r) {      // fast-forward (LF_table.hpp:256-259)
+        L.off -= len;
+        ++L.addr;
+        return;
+    }
+    // settled on (addr, off): process the next base
+    const uint32_t jj = --L.j;
+    uint32_t code;
+    uint8_t cbyte = 0;
+    if (PACKED) {
+        code = (L.rw >> (2 * (jj & 15))) & 3u;
+        if ((jj & 15) == 0 && jj != 0) L.rw = ld_ro(bv.words + L.in_off + ((jj - 1) >> 4));
+    } else {
+        cbyte = ld_ro(bv.bytes + L.in_off + jj);
+        code = code_lut[cbyte];
+    }
+    const uint32_t chc = row_chc(row);
+    const uint32_t cid = row_cid(row);          // sampled before any reposition (col_bwt.hpp:513)
+    bool match = (code == chc);
+    if (!PACKED && code >= CODE_OTHER)
+        match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
+    if (match) {
+        ++L.plen;                                // col_bwt.hpp:516-518
+    } else {
+        L.plen = 0;                              // col_bwt.hpp:520-523
+    }
+    lane_emit(L, bv, jj, L.plen, cid);
+    if (jj == 0) {                               // the reference's last LF step has no observable effect
+        L.state = LANE_IDLE;
+        return;
+    }
+    if (!match) {
+        bool found = false, use_pred = false;
+        uint32_t tgt = 0;
+        if (PACKED || code < CODE_OTHER) {
+            const uint64_t meta = row_meta(row);
+            const uint32_t slot = (code - chc - 1u) & 3u;
+            const uint32_t mode = (uint32_t)(meta >> (11 + 2 * slot)) & 3u;
+            if (mode == 3) {
+                found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+            } else {
+                const uint32_t d = (uint32_t)(meta >> (17 + 10 * slot)) & 1023u;
+                const uint32_t fx = (uint32_t)(meta >> 47) & 0xFFFFu;
+                use_pred = (mode == 1) || (mode == 2 && L.off < fx);
+                tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
+                found = true;
+            }
+        } else if (code == CODE_OTHER) {
+            found = slow_reposition(t, L.addr, L.off, cbyte, &tgt, &use_pred);
+        }
+        if (found) {
+            L.addr = tgt;
+            L.state = use_pred ? LANE_REPOS_PRED : LANE_REPOS_SUCC;
+            return;
+        }
+        // nothing found: state kept, LF proceeds through the current row (col_bwt.hpp:572-573)
+    }
+    L.off = row_doff(row) + L.off;               // LF_table.hpp:253-254
+    L.addr = row.dest;
+}
+
+} // namespace colbwt

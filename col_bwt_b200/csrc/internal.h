@@ -1,0 +1,67 @@
+// internal.h -- host-side structures shared by index.cu / query.cu / capi.cpp (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/colbwt_b200.h"
+#include "colbwt_core.cuh"
+
+namespace colbwt {
+
+void set_error(const char *fmt, ...);
+
+#define CB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            colbwt::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));      \
+            return COLBWT_ERR_CUDA;                                                                     \
+        }                                                                                               \
+    } while (0)
+
+// The table in the HBM of one GPU.
+struct DeviceTable {
+    int device = -1;
+    TableView view{};
+    void *d_rows = nullptr, *d_ch8 = nullptr, *d_idx = nullptr, *d_thr = nullptr, *d_char_rows = nullptr,
+         *d_char_start = nullptr, *d_code_lut = nullptr;
+    uint64_t bytes = 0;
+    int sm_count = 0;
+};
+
+} // namespace colbwt
+
+namespace colbwt { struct Pipeline; void destroy_pipeline(Pipeline *); }
+
+struct colbwt_index {
+    colbwt_stats stats{};
+    std::vector<colbwt::DeviceTable> dev;
+    uint8_t code_lut[256];
+    std::mutex query_mutex;                 // one colbwt_query at a time per index
+    colbwt::Pipeline *pipeline = nullptr;   // staging buffers + streams, kept between colbwt_query calls
+};
+
+namespace colbwt {
+
+// index.cu: upload + device-side build of one replica from the raw 18-byte rows (host memory, or streamed
+// from `fp` when rows == nullptr).
+int build_device_table(DeviceTable &dt, int device, const void *rows, FILE *fp, uint64_t n, uint64_t r,
+                       colbwt_stats *stats, uint8_t *code_lut_out);
+void free_device_table(DeviceTable &dt);
+
+// pack.cpp: host-side 2-bit packer.
+// Packs reads [r0, r1) of a batch: 2-bit words at word offsets word_off[i] (relative to words),
+// returns false for reads that contain a byte outside ACGT (their words are garbage, caller ships bytes).
+bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
+
+// kernels (index.cu / traverse.cu) launched through these host wrappers
+int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_counters,
+                    cudaStream_t stream);
+
+} // namespace colbwt

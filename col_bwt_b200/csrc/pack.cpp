@@ -1,0 +1,88 @@
+// pack.cpp -- host-side 2-bit packing of reads (the input format the traversal kernel streams from HBM).
+//
+// Replaces the byte-at-a-time access `pattern[m - i - 1]` of include/col_bwt.hpp:512: a read made only of
+// A/C/G/T is stored 2 bit/base, code = (byte >> 1) & 3 (A=0 C=1 T=2 G=3), 16 bases per little-endian 32-bit
+// word, base j at bits 2*(j & 15) of word j >> 4.  Any other byte (N, lower case, IUPAC, ...) makes the read
+// "irregular": it is shipped as raw bytes and traversed by the byte kernel, so comparisons stay byte-exact.
+#include <cstdint>
+#include <cstring>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace colbwt {
+
+static inline bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+#if defined(__x86_64__)
+// 32 bases -> 64 bits.  Returns false if any byte is outside ACGT.
+__attribute__((target("avx2"))) static inline bool pack32_avx2(const uint8_t *p, uint64_t *out)
+{
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+    const __m256i code = _mm256_and_si256(_mm256_srli_epi16(x, 1), _mm256_set1_epi8(3));
+    // expected byte for each code: 0->A 1->C 2->T 3->G
+    const __m256i lut = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                         'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i expect = _mm256_shuffle_epi8(lut, code);
+    const bool ok = _mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, x)) == -1;
+    // pairs of bytes -> 4 bit, pairs of those -> 8 bit
+    const __m256i n4 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));          // b0 + 4*b1 in each 16-bit lane
+    const __m256i n8 = _mm256_madd_epi16(n4, _mm256_set1_epi32(0x00100001));           // lo + 16*hi in each 32-bit lane
+    // gather the low byte of the 8 dwords: within each 128-bit half bytes 0,4,8,12
+    const __m256i sh = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                        0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i g = _mm256_shuffle_epi8(n8, sh);
+    const uint32_t lo = (uint32_t)_mm256_extract_epi32(g, 0), hi = (uint32_t)_mm256_extract_epi32(g, 4);
+    *out = (uint64_t)lo | ((uint64_t)hi << 32);
+    return ok;
+}
+
+__attribute__((target("avx2"))) static bool pack_avx2(const uint8_t *seq, uint64_t len, uint32_t *words)
+{
+    bool ok = true;
+    uint64_t j = 0;
+    for (; j + 32 <= len; j += 32) {
+        uint64_t w;
+        ok &= pack32_avx2(seq + j, &w);
+        memcpy(words + (j >> 4), &w, 8);
+    }
+    if (j < len) {
+        uint8_t tail[32];
+        memset(tail, 'A', sizeof(tail));
+        memcpy(tail, seq + j, len - j);
+        uint64_t w;
+        ok &= pack32_avx2(tail, &w);
+        const uint64_t nwords = (len - j + 15) >> 4;
+        memcpy(words + (j >> 4), &w, nwords * 4);
+    }
+    return ok;
+}
+#endif
+
+static bool pack_scalar(const uint8_t *seq, uint64_t len, uint32_t *words)
+{
+    bool ok = true;
+    for (uint64_t w = 0; w * 16 < len; ++w) {
+        uint32_t v = 0;
+        const uint64_t e = (len - w * 16 < 16) ? len - w * 16 : 16;
+        for (uint64_t k = 0; k < e; ++k) {
+            const uint8_t c = seq[w * 16 + k];
+            ok &= is_acgt(c);
+            v |= (uint32_t)((c >> 1) & 3) << (2 * k);
+        }
+        words[w] = v;
+    }
+    return ok;
+}
+
+bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words)
+{
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return pack_avx2(seq, len, words);
+#endif
+    return pack_scalar(seq, len, words);
+}
+
+} // namespace colbwt

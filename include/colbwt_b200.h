@@ -1,0 +1,126 @@
+/* colbwt_b200.h -- C-ABI of the B200-native col-bwt query path (PML + chain ids per base).
+ *
+ * The reference (drnatebrown/col-bwt) has no FFI; its boundary for this path is the C++ class
+ * `col_pml` plus the `pml_query` executable.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference tree):
+ *
+ *   colbwt_index_load        col_pml::load / col_bwt::load           include/col_bwt.hpp:375-380
+ *                            + LF_table::load                        include/ds/LF_table.hpp:347-357
+ *                            (called from src/pml_query.cpp:110-113)
+ *   colbwt_index_from_rows   the same, from memory (rows as read_vec would fill them,
+ *                            include/common/common.hpp:318-323)
+ *   colbwt_index_stats       col_bwt::bwt_stats / runs / size        include/col_bwt.hpp:331-344
+ *   colbwt_query             col_pml::query_pml(const char*, size_t) include/col_bwt.hpp:409-412, for a whole
+ *                            batch of reads (the per-read loop of src/pml_query.cpp:74-86)
+ *   colbwt_batch_*           the same split into upload / traverse / download so the traversal can be
+ *                            timed with its inputs resident in HBM
+ *   colbwt_format_stats      the text writer of pml_to_vec           src/pml_query.cpp:79-85
+ *
+ * Plain pointers and sizes only.  All functions return COLBWT_OK (0) or a negative colbwt_status;
+ * colbwt_last_error() gives a message for the calling thread.  There is no CPU fallback: without a CUDA
+ * device every entry point that computes returns COLBWT_ERR_CUDA.
+ *
+ * Semantics (bit-exact with the reference, SURVEY.md section 8a checklist): reads are raw bytes, compared
+ * byte-exactly with the row characters; outputs are indexed by read position, pml[off[i]+j] / cid[off[i]+j]
+ * for base j of read i; a zero-length read produces no values.
+ */
+#ifndef COLBWT_B200_H
+#define COLBWT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum colbwt_status {
+    COLBWT_OK = 0,
+    COLBWT_ERR_IO = -1,          /* file missing or short                                   */
+    COLBWT_ERR_FORMAT = -2,      /* header inconsistent (size != r, r == 0, r >= 2^32)      */
+    COLBWT_ERR_ROW_TOO_LONG = -3,/* a row of >= 65536 symbols (16-bit offset field wraps in the reference, LF_table.hpp:39) */
+    COLBWT_ERR_CUDA = -4,        /* no device / CUDA runtime failure                        */
+    COLBWT_ERR_ARG = -5,         /* bad argument (null pointer, PML width too small, ...)   */
+    COLBWT_ERR_NOMEM = -6
+} colbwt_status;
+
+typedef struct colbwt_index colbwt_index;   /* move table replicated in the HBM of one or more GPUs */
+typedef struct colbwt_batch colbwt_batch;   /* one batch of reads resident on one GPU               */
+
+typedef struct colbwt_stats {
+    uint64_t n;            /* BWT length                        (LF_table.hpp:359) */
+    uint64_t r;            /* rows = sub-runs                   (LF_table.hpp:360) */
+    uint64_t bwt_r;        /* BWT runs before sub-run splitting (col_bwt.hpp:382)  */
+    uint64_t marked_rows;  /* rows with col_id != 0                                 */
+    uint64_t slow_rows;    /* rows whose reposition data did not fit the packed row (resolved by exact search) */
+    uint64_t device_bytes; /* HBM bytes held per device                              */
+    uint32_t max_row_len;
+    int32_t  n_devices;
+} colbwt_stats;
+
+/* Width in bytes of one PML value in caller buffers: 2 (reads shorter than 65536) or 4. */
+#define COLBWT_PML_U16 2
+#define COLBWT_PML_U32 4
+
+/* ---- index ------------------------------------------------------------------------------------------- */
+
+/* Load PATH (the reference's `<prefix>.col_pml`; if PATH does not exist, PATH + ".col_pml" is tried, which
+ * is how pml_query.cpp:110-111 forms the name) and upload it to `n_devices` GPUs (`devices[i]` = CUDA
+ * ordinal; devices == NULL means 0..n_devices-1). */
+int colbwt_index_load(const char *path, const int *devices, int n_devices, colbwt_index **out);
+
+/* Same from memory: `rows` = r packed 18-byte col_thr rows exactly as they sit in the file. */
+int colbwt_index_from_rows(const void *rows, uint64_t bwt_r, uint64_t n, uint64_t r,
+                           const int *devices, int n_devices, colbwt_index **out);
+
+int colbwt_index_stats(const colbwt_index *idx, colbwt_stats *out);
+void colbwt_index_free(colbwt_index *idx);
+
+/* ---- query, host buffers (the drop-in call) ------------------------------------------------------------ */
+
+/* n_reads reads: bytes seqs[off[i] .. off[i+1]).  pml has off[n_reads] elements of `pml_width` bytes, cid has
+ * off[n_reads] bytes.  Reads are packed on the host (2 bit/base; reads with a byte outside ACGT travel as
+ * bytes), streamed through pinned double-buffered copies, traversed on the GPU(s) and the results copied back
+ * in input order.  With several devices, chunks of reads are dealt round-robin; no inter-GPU communication. */
+int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
+                 void *pml, int pml_width, uint8_t *cid);
+
+/* Pinned host memory for seqs / pml / cid buffers (lets colbwt_query copy without a staging hop). */
+void *colbwt_host_alloc(size_t bytes);
+void colbwt_host_free(void *p);
+
+/* ---- query, device-resident batch (for kernel-only timing and for callers that keep results on device) -- */
+
+int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uint8_t *seqs, const uint64_t *off,
+                        uint64_t n_reads, int pml_width, colbwt_batch **out);
+/* Run the traversal `iters` times back to back; *ms_per_iter (may be NULL) = CUDA-event time / iters measured
+ * on the launching stream.  Outputs stay on the device. */
+int colbwt_batch_run(colbwt_batch *b, int iters, float *ms_per_iter);
+int colbwt_batch_download(colbwt_batch *b, void *pml, uint8_t *cid);
+/* Device pointers of the results (pml: pml_width-byte elements, cid: bytes), valid until colbwt_batch_free. */
+int colbwt_batch_device_ptrs(colbwt_batch *b, void **pml_dev, void **cid_dev, uint64_t *n_bases);
+/* Kernel launches issued by one traversal of this batch (for bench.py's gpu_launches). */
+int colbwt_batch_launches(const colbwt_batch *b);
+void colbwt_batch_free(colbwt_batch *b);
+
+/* ---- text output of pml_query (src/pml_query.cpp:79-85) -------------------------------------------------- */
+
+/* Formats one read: ">" id " \n", every value followed by " ", then "\n".  Returns bytes written, or the
+ * bytes needed if cap is too small (nothing is written then).  width = element bytes of `values` (1, 2, 4). */
+size_t colbwt_format_stats(char *buf, size_t cap, const char *id, size_t id_len,
+                           const void *values, int width, uint64_t m);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------- */
+
+/* Random-gather roofline microbenchmark on `device`: `loads` independent 16-byte loads, each from a random
+ * 32-byte sector of a `bytes`-sized buffer.  dependent != 0 chains each thread's next address on the loaded
+ * value (latency-bound variant with the same occupancy).  *sectors_per_s receives the measured rate. */
+int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, int dependent, double *sectors_per_s);
+
+const char *colbwt_last_error(void);
+const char *colbwt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLBWT_B200_H */

@@ -150,3 +150,64 @@ def sample_reads(text: np.ndarray, seq_starts: np.ndarray, n_reads: int, read_le
         out.append(rd)
         offsets[i + 1] = offsets[i] + np.uint64(rd.size)
     return (np.concatenate(out) if out else np.zeros(0, np.uint8)), offsets
+
+
+def sample_reads_device(text, seq_starts: np.ndarray, n_reads: int, read_len: int, *, sub: float = 0.01, ins: float = 0.0,
+                        dele: float = 0.0, seed: int = 2, len_sigma: float = 0.0, device="cuda", chunk_bases: int = 1 << 28):
+    """torch version of sample_reads for bench-scale batches (1e9+ bases), generated on `device` in chunks.
+
+    Error model: every output base advances the source position by 1 (plain), 0 (insertion: the base is random) or
+    2 (deletion: one source base skipped); substitutions replace the base by a different one.  len_sigma > 0 draws
+    read lengths from a log-normal around read_len.  Returns host numpy (seqs u8, offsets u64)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    txt = torch.as_tensor(text, device=dev)
+    ss = torch.as_tensor(seq_starts, device=dev)
+    n_seq = ss.numel() - 1
+    seq_len = ss[1:] - ss[:-1] - 1
+    min_seq = int(seq_len.min())
+    if len_sigma > 0:
+        z = torch.randn(n_reads, generator=g, device=dev)
+        lens = (read_len * torch.exp(len_sigma * z - 0.5 * len_sigma * len_sigma)).long().clamp(32, int(min_seq / 1.2))
+    else:
+        lens = torch.full((n_reads,), min(read_len, int(min_seq / 1.2)), dtype=torch.long, device=dev)
+    offsets = torch.zeros(n_reads + 1, dtype=torch.long, device=dev)
+    offsets[1:] = torch.cumsum(lens, 0)
+    total = int(offsets[-1])
+    out = np.empty(total, dtype=np.uint8)
+    acgt = torch.as_tensor(ACGT, device=dev)
+    code_of = torch.zeros(256, dtype=torch.long, device=dev)
+    code_of[acgt.long()] = torch.arange(4, device=dev)
+    off_host = offsets.cpu().numpy()
+    r0 = 0
+    while r0 < n_reads:
+        r1 = int(np.searchsorted(off_host, off_host[r0] + chunk_bases, side="right")) - 1
+        r1 = min(max(r1, r0 + 1), n_reads)
+        ln = lens[r0:r1]
+        nb = int(off_host[r1] - off_host[r0])
+        rid = torch.repeat_interleave(torch.arange(r1 - r0, device=dev), ln)
+        which = torch.randint(0, n_seq, (r1 - r0,), generator=g, device=dev)
+        span = (ln.double() * (1.0 + 1.5 * dele) + 8).long()          # source bases a read may consume
+        room = (seq_len[which] - span).clamp(min=1)
+        start = ss[which] + (torch.rand(r1 - r0, generator=g, device=dev, dtype=torch.float64) * room.double()).long()
+        u = torch.rand(nb, generator=g, device=dev)
+        step = torch.ones(nb, dtype=torch.long, device=dev)
+        is_ins = u < ins
+        step[is_ins] = 0
+        step[(u >= ins) & (u < ins + dele)] = 2
+        cs = torch.cumsum(step, 0)
+        first = (offsets[r0:r1] - offsets[r0])                          # chunk-local first base of each read
+        base_cs = cs[first] - step[first]
+        src = start[rid] + (cs - step) - base_cs[rid]
+        last_ok = (ss[which + 1] - 2)[rid]
+        b = txt[torch.minimum(src, last_ok)]
+        rnd = acgt[torch.randint(0, 4, (nb,), generator=g, device=dev)]
+        b = torch.where(is_ins, rnd, b)
+        is_sub = torch.rand(nb, generator=g, device=dev) < sub
+        rot = torch.randint(1, 4, (nb,), generator=g, device=dev)
+        b = torch.where(is_sub, acgt[(code_of[b.long()] + rot) & 3], b)
+        out[off_host[r0]:off_host[r1]] = b.cpu().numpy()
+        r0 = r1
+    return out, off_host.astype(np.uint64)

@@ -148,7 +148,8 @@ def resolve_marks_fast(n: int, run_starts: np.ndarray, starts: np.ndarray, ids: 
     return pos[lastp].astype(np.uint64), idv[lastp].astype(np.uint8)
 
 
-def build_columns(heads: np.ndarray, lens: np.ndarray, thr: np.ndarray, split_pos: np.ndarray, split_ids: np.ndarray):
+def build_columns(heads: np.ndarray, lens: np.ndarray, thr: np.ndarray, split_pos: np.ndarray, split_ids: np.ndarray,
+                  strict: bool = True):
     """Columns of the `.col_pml` table from the primaries, as the reference constructs them.
 
     heads/lens/thr: per BWT run.  split_pos/split_ids: set bits of `.col_runs` (must include every run head,
@@ -172,9 +173,9 @@ def build_columns(heads: np.ndarray, lens: np.ndarray, thr: np.ndarray, split_po
     fpos[order] = np.cumsum(row_len[order]) - row_len[order]
     interval = np.searchsorted(idx, fpos, side="right") - 1
     offset = fpos - idx[interval]
-    assert offset.max(initial=0) < 65536 and idx.size < 2**32, "16-bit offset / 32-bit interval fields would wrap"
+    assert not strict or (offset.max(initial=0) < 65536 and idx.size < 2**32), "16-bit offset / 32-bit interval fields would wrap"
     return {
         "ch": ch, "idx": idx.astype(np.uint64), "interval": interval.astype(np.uint32),
-        "offset": offset.astype(np.uint16), "col_id": col_id, "thr": np.asarray(thr, dtype=np.uint64)[run_of],
+        "offset": (offset & 0xFFFF).astype(np.uint16), "col_id": col_id, "thr": np.asarray(thr, dtype=np.uint64)[run_of],
         "n": n, "bwt_r": int(heads.size),
     }

@@ -1,0 +1,67 @@
+"""ctypes front-end of tests/native/libemulate.so (host emulation of the product's device logic). Test infrastructure."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "native", "libemulate.so")
+SRC = [os.path.join(HERE, "native", "emulate.cpp"), os.path.join(HERE, "..", "col_bwt_b200", "csrc", "pack.cpp")]
+HDR = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "colbwt_core.cuh")
+
+
+def build():
+    newest = max(os.path.getmtime(p) for p in SRC + [HDR])
+    if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRC, check=True)
+
+
+class Emu:
+    def __init__(self, cols: dict):
+        build()
+        L = self.L = C.CDLL(SO)
+        L.emu_build.restype = C.c_void_p
+        L.emu_build.argtypes = [C.c_uint64, C.c_uint64] + [C.c_void_p] * 6
+        L.emu_free.argtypes = [C.c_void_p]
+        L.emu_slow_rows.restype = C.c_uint64
+        L.emu_slow_rows.argtypes = [C.c_void_p]
+        L.emu_flags.restype = C.c_uint32
+        L.emu_flags.argtypes = [C.c_void_p]
+        L.emu_rows.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_query.restype = C.c_uint64
+        L.emu_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.keep = [np.ascontiguousarray(cols["ch"], np.uint8), np.ascontiguousarray(cols["idx"], np.uint64),
+                     np.ascontiguousarray(cols["interval"], np.uint32), np.ascontiguousarray(cols["offset"], np.uint16),
+                     np.ascontiguousarray(cols["col_id"], np.uint8), np.ascontiguousarray(cols["thr"], np.uint64)]
+        self.r = len(self.keep[0])
+        self.h = L.emu_build(int(cols["n"]), self.r, *[a.ctypes.data for a in self.keep])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.emu_free(self.h)
+            self.h = None
+
+    @property
+    def slow_rows(self):
+        return self.L.emu_slow_rows(self.h)
+
+    @property
+    def flags(self):
+        return self.L.emu_flags(self.h)
+
+    def rows(self):
+        out = np.zeros((self.r, 4), np.uint32)
+        self.L.emu_rows(self.h, out.ctypes.data)
+        return out
+
+    def query(self, seqs, offsets, pml_width=2, force_bytes=False):
+        seqs = np.ascontiguousarray(seqs, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        pml = np.zeros(seqs.size + 8, np.uint16 if pml_width == 2 else np.uint32)
+        cid = np.zeros(seqs.size + 8, np.uint8)
+        self.iters = self.L.emu_query(self.h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data,
+                                      pml_width, cid.ctypes.data, int(force_bytes))
+        return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]

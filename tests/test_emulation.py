@@ -1,0 +1,118 @@
+"""CPU: the product's device logic (colbwt_core.cuh row builder + lane state machine, pack.cpp), run lane by lane
+on the host by tests/native/emulate.cpp, against the oracle.  This is how kernel logic is debugged without a GPU;
+the GPU parity tests proper are in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from emu import Emu
+from synthdata import formats as F, pangenome as P, pipeline as PL
+from util import adversarial_reads, check_pml_properties, concat_reads, parse_fastx
+
+
+def cols_from_file(path):
+    meta, rows = F.read_col_pml(path)
+    return {"ch": rows["ch"], "idx": F.u40_unpack(rows["idx"]), "interval": rows["interval"], "offset": rows["offset"],
+            "col_id": rows["col_id"], "thr": F.u40_unpack(rows["thr"]), "n": meta["n"], "bwt_r": meta["bwt_r"]}
+
+
+@pytest.mark.parametrize("case", ["toy", "pan4"])
+@pytest.mark.parametrize("width", [2, 4])
+@pytest.mark.parametrize("force_bytes", [False, True])
+def test_emulated_kernel_logic_on_golden(golden_dir, case, width, force_bytes):
+    path = os.path.join(golden_dir, f"{case}.col_pml")
+    orc = oracle.Oracle(path)
+    emu = Emu(cols_from_file(path))
+    ids, seqs, off = parse_fastx(os.path.join(golden_dir, f"{case}_reads.fa"))
+    p0, c0 = orc.query_batch(seqs, off)
+    p1, c1 = emu.query(seqs, off, pml_width=width, force_bytes=force_bytes)
+    assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+
+
+def test_emulated_kernel_logic_on_synthetic(small_index):
+    orc = oracle.Oracle(small_index["path"])
+    emu = Emu(small_index["cols"])
+    assert emu.flags & 1 == 0
+    extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
+    for seqs, off in ((small_index["seqs"], small_index["off"]), (extra, eoff)):
+        p0, c0 = orc.query_batch(seqs, off)
+        for fb in (False, True):
+            p1, c1 = emu.query(seqs, off, force_bytes=fb)
+            assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+        check_pml_properties(p1, off)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulated_random_tables_small_alphabet_quirks(seed):
+    """Degenerate tables: tiny genomes, high divergence, a haplotype with N runs and lower case, no marks / dense marks."""
+    rng = np.random.default_rng(seed)
+    haps = P.make_haplotypes(int(rng.integers(300, 3000)), int(rng.integers(2, 5)), snp=0.03, indel=0.005, seed=seed)
+    if seed == 2:   # N run and lower-case stretch inside the text: rows with "other" characters
+        h = haps[0].copy()
+        h[50:60] = ord("N")
+        h[100:120] = np.frombuffer(bytes(h[100:120]).lower(), np.uint8)
+        haps[0] = h
+    idx = PL.build_index(haps, split_rate=int(rng.integers(1, 4)), min_mum=8)
+    cols = idx["columns"]
+    orc = oracle.Oracle(columns=cols)
+    emu = Emu(cols)
+    seqs, off = P.sample_reads(idx["text"], idx["seq_starts"], 300, 80, sub=0.05, seed=seed)
+    extra, eoff = concat_reads(adversarial_reads(haps))
+    for s, o in ((seqs, off), (extra, eoff)):
+        p0, c0 = orc.query_batch(s, o)
+        p1, c1 = emu.query(s, o)
+        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+
+
+def test_far_reposition_targets_take_exact_search():
+    """A table where the next row of some character is > 31 rows away (distance fields overflow)."""
+    rng = np.random.default_rng(5)
+    # text: long stretch alternating A/C only, then G/T region => BWT has regions without G rows
+    a = np.frombuffer(b"AC", np.uint8)[rng.integers(0, 2, 4000)]
+    b = P.ACGT[rng.integers(0, 4, 500)]
+    idx = PL.build_index([np.concatenate((a, b)), np.concatenate((a[::-1], b))], with_revcomp=False, marks=False)
+    cols = idx["columns"]
+    emu = Emu(cols)
+    assert emu.slow_rows > 10
+    orc = oracle.Oracle(columns=cols)
+    reads = [bytes(a[100:200]) + b"G" + bytes(a[300:330]), b"GGGG" + bytes(a[5:50]) + b"T", bytes(b[10:90])]
+    s, o = concat_reads(reads)
+    p0, c0 = orc.query_batch(s, o)
+    p1, c1 = emu.query(s, o)
+    assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+
+
+def test_row_builder_flags_overlong_rows():
+    # one run of 70000 A's: a row longer than the 16-bit offset field can address
+    text = np.concatenate((np.full(70000, ord("A"), np.uint8), np.frombuffer(b"CGT\x00", np.uint8)))
+    from synthdata import bwtbuild as B, table as T
+    si = B.SuffixIndex(text)
+    bwt = si.bwt()
+    heads, starts, lens = B.bwt_runs(bwt)
+    thr = B.thresholds(bwt, si.lcp(), heads, starts)
+    cols = T.build_columns(heads.numpy(), lens.numpy(), thr.numpy(), starts.numpy(), np.zeros(starts.numel(), np.uint8), strict=False)
+    assert Emu(cols).flags & 1
+
+
+def test_host_packer_matches_scalar_definition():
+    import ctypes as C
+    from emu import SO, build
+    build()
+    L = C.CDLL(SO)
+    L.emu_pack.restype = C.c_int
+    L.emu_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(0)
+    for n in (1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 150, 1000):
+        s = P.ACGT[rng.integers(0, 4, n)]
+        w = np.zeros((n + 15) // 16 + 2, np.uint32)
+        assert L.emu_pack(s.ctypes.data, n, w.ctypes.data) == 1
+        code = (s >> 1) & 3
+        for j in range(n):
+            assert (int(w[j >> 4]) >> (2 * (j & 15))) & 3 == code[j]
+        for bad in (b"N", b"a", b"\x00", b"U"):
+            for pos in (0, n // 2, n - 1):
+                t = s.copy()
+                t[pos] = bad[0]
+                assert L.emu_pack(t.ctypes.data, n, w.ctypes.data) == 0

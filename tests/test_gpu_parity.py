@@ -1,0 +1,230 @@
+"""GPU (-m gpu): parity of the CUDA path with the oracle, through the C-ABI (col_bwt_b200 -> libcolbwt_b200.so).
+
+Bit-exact is the bar: PML and chain ids are integers.  Reads nothing from /root/reference."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from synthdata import formats as F, pangenome as P, pipeline as PL
+from util import adversarial_reads, check_pml_properties, concat_reads, parse_fastx
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import col_bwt_b200
+    return col_bwt_b200
+
+
+@pytest.mark.parametrize("case", ["toy", "pan4"])
+def test_golden_text_matches_reference_pml_query(cb, golden_dir, case):
+    """Golden .pml/.cid are the bytes the reference's pml_query wrote; format through the C-ABI and compare bytes."""
+    tbl = cb.ColPml.load(os.path.join(golden_dir, f"{case}.col_pml"))
+    ids, seqs, off = parse_fastx(os.path.join(golden_dir, f"{case}_reads.fa"))
+    for width in (cb.PML_U16, cb.PML_U32):
+        pml, cid = tbl.query(seqs, off, width)
+        txt_p = b"".join(cb.format_stats(ids[i], pml[int(off[i]):int(off[i + 1])]) for i in range(len(ids)))
+        txt_c = b"".join(cb.format_stats(ids[i], cid[int(off[i]):int(off[i + 1])]) for i in range(len(ids)))
+        assert txt_p == open(os.path.join(golden_dir, f"{case}_reads.fa.pml"), "rb").read()
+        assert txt_c == open(os.path.join(golden_dir, f"{case}_reads.fa.cid"), "rb").read()
+
+
+def test_query_pml_single_read_api(cb, golden_dir):
+    tbl = cb.ColPml.load(os.path.join(golden_dir, "toy"))      # prefix form, as pml_query.cpp:110-111
+    assert (tbl.n, tbl.r, tbl.bwt_r) == (43, 28, 22)
+    pml, cid = tbl.query_pml("GATTACAGAT")
+    assert pml.tolist() == [6, 5, 4, 3, 2, 1, 0, 2, 1, 0] and cid.tolist() == [0, 10, 0, 0, 6, 4, 0, 0, 0, 0]
+    pml, cid = tbl.query_pml(b"TTAGGATNACA")
+    assert pml.tolist() == [1, 0, 1, 0, 3, 2, 1, 0, 1, 0, 1] and cid.tolist() == [0, 0, 0, 7, 5, 9, 0, 0, 0, 0, 0]
+    pml, cid = tbl.query_pml(b"")
+    assert pml.size == 0 and cid.size == 0
+
+
+def test_synthetic_index_vs_oracle_all_paths(cb, small_index):
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    assert tbl.r == len(small_index["cols"]["ch"])
+    extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
+    for seqs, off in ((small_index["seqs"], small_index["off"]), (extra, eoff)):
+        want_p, want_c = orc.query_batch(seqs, off)
+        for width in (cb.PML_U16, cb.PML_U32):
+            pml, cid = tbl.query(seqs, off, width)
+            assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+            b = tbl.batch(seqs, off, width)
+            b.run(2)
+            p2, c2 = b.download()
+            assert np.array_equal(p2.astype(np.uint32), want_p) and np.array_equal(c2, want_c)
+            b.close()
+        check_pml_properties(pml, off)
+
+
+def test_mixed_batch_regular_and_irregular_reads_keep_input_order(cb, small_index):
+    rng = np.random.default_rng(4)
+    seqs = small_index["seqs"].copy()
+    off = small_index["off"]
+    # sprinkle N / lower case into ~10 % of the reads
+    for i in rng.choice(len(off) - 1, (len(off) - 1) // 10, replace=False):
+        a, b = int(off[i]), int(off[i + 1])
+        seqs[a + int(rng.integers(0, b - a))] = ord("N") if rng.random() < 0.5 else ord("a")
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_streaming_chunks_and_pinned_buffers(cb, small_index, monkeypatch):
+    """Many small chunks through the 3-slot pipeline, pageable and pinned output buffers."""
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "20000")
+    seqs, off = small_index["seqs"], small_index["off"]
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    pp, pc = cb.PinnedArray(seqs.size, np.uint16), cb.PinnedArray(seqs.size, np.uint8)
+    tbl.query(seqs, off, out=(pp.array, pc.array))
+    assert np.array_equal(pp.array.astype(np.uint32), want_p) and np.array_equal(pc.array, want_c)
+    # a second call reuses the cached pipeline
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_variable_lengths_and_long_reads_u32(cb, small_index):
+    """Reads from 1 base to > 65535 bases in one batch (PML needs 32 bits)."""
+    idx = small_index["idx"]
+    rng = np.random.default_rng(8)
+    hap = np.concatenate([small_index["haps"][k % 4] for k in range(3)])
+    long_read = hap[:70000].copy()
+    pos = rng.integers(0, long_read.size, 700)
+    long_read[pos] = P.ACGT[rng.integers(0, 4, 700)]
+    reads = [bytes(long_read)]
+    s, o = P.sample_reads(idx["text"], idx["seq_starts"], 400, 600, sub=0.03, seed=5, len_jitter=0.8)
+    reads += [bytes(s[int(o[i]):int(o[i + 1])]) for i in range(len(o) - 1)]
+    reads += [b"A", b"", b"CG"]
+    seqs, off = concat_reads(reads)
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(seqs, off, cb.PML_U32)
+    assert np.array_equal(pml, want_p) and np.array_equal(cid, want_c)
+    with pytest.raises(cb.ColBwtError) as e:
+        tbl.query(seqs, off, cb.PML_U16)
+    assert e.value.code == -5
+
+
+def test_nanopore_like_reads_with_indels(cb, small_index):
+    idx = small_index["idx"]
+    seqs, off = P.sample_reads(idx["text"], idx["seq_starts"], 60, 4000, sub=0.02, ins=0.015, dele=0.015, seed=6, len_jitter=0.3)
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_table_with_other_characters_and_far_targets(cb, tmp_path):
+    """Rows carrying N / lower case, and regions where a character's next row is > 31 rows away."""
+    rng = np.random.default_rng(5)
+    a = np.frombuffer(b"AC", np.uint8)[rng.integers(0, 2, 4000)]
+    b = P.ACGT[rng.integers(0, 4, 500)].copy()
+    b[100:110] = ord("N")
+    b[200:230] = np.frombuffer(bytes(b[200:230]).lower(), np.uint8)
+    idx = PL.build_index([np.concatenate((a, b)), np.concatenate((a[::-1], b))], with_revcomp=False, marks=False)
+    path = str(tmp_path / "odd.col_pml")
+    PL.write_col_pml(path, idx["columns"])
+    reads = [bytes(a[100:200]) + b"G" + bytes(a[300:330]), b"GGGG" + bytes(a[5:50]) + b"T", bytes(b[10:300]), bytes(b[90:120]),
+             b"NNNNNNNNNNNN", bytes(b[195:240])] + adversarial_reads()
+    seqs, off = concat_reads(reads)
+    want_p, want_c = oracle.Oracle(path).query_batch(seqs, off)
+    tbl = cb.ColPml.load(path)
+    assert tbl.stats.slow_rows > 10
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_from_rows_equals_load(cb, small_index):
+    meta, rows = F.read_col_pml(small_index["path"])
+    t1 = cb.ColPml.from_rows(rows, meta["bwt_r"], meta["n"])
+    t2 = cb.ColPml.load(small_index["path"])
+    seqs, off = small_index["seqs"][:30000], small_index["off"][:201]
+    p1, c1 = t1.query(seqs, off)
+    p2, c2 = t2.query(seqs, off)
+    assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+    assert t1.stats.marked_rows == int((small_index["cols"]["col_id"] > 0).sum())
+
+
+def test_error_codes(cb, tmp_path, golden_dir):
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.load(str(tmp_path / "missing"))
+    assert e.value.code == -1
+    data = open(os.path.join(golden_dir, "toy.col_pml"), "rb").read()
+    (tmp_path / "short.col_pml").write_bytes(data[:200])
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.load(str(tmp_path / "short.col_pml"))
+    assert e.value.code == -1
+    hdr = np.frombuffer(data[:32], "<u8").copy()
+    hdr[3] += 1                                                   # size != r
+    (tmp_path / "bad.col_pml").write_bytes(hdr.tobytes() + data[32:])
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.load(str(tmp_path / "bad.col_pml"))
+    assert e.value.code == -2
+    # a row of 70000 symbols cannot be addressed by the reference's 16-bit offset field
+    from synthdata import bwtbuild as B, table as T
+    text = np.concatenate((np.full(70000, ord("A"), np.uint8), np.frombuffer(b"CGT\x00", np.uint8)))
+    si = B.SuffixIndex(text)
+    bwt = si.bwt()
+    heads, starts, lens = B.bwt_runs(bwt)
+    thr = B.thresholds(bwt, si.lcp(), heads, starts)
+    cols = T.build_columns(heads.numpy(), lens.numpy(), thr.numpy(), starts.numpy(), np.zeros(starts.numel(), np.uint8), strict=False)
+    rows = F.rows_from_columns(cols["ch"], cols["idx"], cols["interval"], cols["offset"], cols["col_id"], cols["thr"])
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.from_rows(rows, cols["bwt_r"], cols["n"])
+    assert e.value.code == -3
+
+
+def test_cli_is_a_drop_in_for_pml_query(golden_dir, tmp_path):
+    """pml_query_b200 <prefix> -p <reads> writes the same two text files as the reference's pml_query."""
+    import shutil
+    for f in ("pan4.col_pml", "pan4_reads.fa"):
+        shutil.copy(os.path.join(golden_dir, f), tmp_path / f)
+    cli = os.path.join(ROOT, "col_bwt_b200", "bin", "pml_query_b200")
+    r = subprocess.run([cli, str(tmp_path / "pan4"), "-p", str(tmp_path / "pan4_reads.fa"), "-v"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "pan4_reads.fa.pml").read_bytes() == open(os.path.join(golden_dir, "pan4_reads.fa.pml"), "rb").read()
+    assert (tmp_path / "pan4_reads.fa.cid").read_bytes() == open(os.path.join(golden_dir, "pan4_reads.fa.cid"), "rb").read()
+    # gzip input, FASTQ records
+    import gzip
+    ids, seqs, off = parse_fastx(os.path.join(golden_dir, "pan4_reads.fa"))
+    with gzip.open(tmp_path / "r.fq.gz", "wb") as f:
+        for i, name in enumerate(ids[:40]):
+            s = bytes(seqs[int(off[i]):int(off[i + 1])])
+            f.write(b"@" + name.encode() + b" c\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    r = subprocess.run([cli, str(tmp_path / "pan4"), "-p", str(tmp_path / "r.fq.gz")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    golden = open(os.path.join(golden_dir, "pan4_reads.fa.pml"), "rb").read().split(b"\n")
+    assert (tmp_path / "r.fq.gz.pml").read_bytes().split(b"\n")[:80] == golden[:80]
+    # failure: non-zero exit code and no output files (col-bwt.py:70-77 behaviour)
+    r = subprocess.run([cli, str(tmp_path / "nope"), "-p", str(tmp_path / "pan4_reads.fa")], capture_output=True, text=True)
+    assert r.returncode != 0
+
+
+def test_config1_scale_properties_and_oracle_sample(cb, tmp_path):
+    """BASELINE.json configs[0] shape scaled to test time: 4 haplotypes x 250 kbp (+revcomp), tunnels -s 10,
+    100k x 150 bp reads; full-size invariants on every base plus oracle parity on a read sample."""
+    haps = P.make_haplotypes(250000, 4, snp=1e-3, seed=1)
+    idx = PL.build_index(haps, split_rate=10)
+    path = str(tmp_path / "c1.col_pml")
+    PL.write_col_pml(path, idx["columns"])
+    seqs, off = P.sample_reads(idx["text"], idx["seq_starts"], 100000, 150, sub=0.01, seed=2)
+    tbl = cb.ColPml.load(path)
+    pml, cid = tbl.query(seqs, off)
+    p2d = pml.reshape(-1, 150).astype(np.int64)
+    assert (p2d <= 150 - np.arange(150)[None, :]).all()
+    nxt = np.concatenate((p2d[:, 1:], np.zeros((p2d.shape[0], 1), np.int64)), axis=1)
+    assert ((p2d == 0) | (p2d == nxt + 1)).all()
+    assert cid.max() > 0 and set(np.unique(cid)) <= set(np.unique(idx["columns"]["col_id"]))
+    k = 20000
+    want_p, want_c = oracle.Oracle(path).query_batch(seqs[: k * 150], off[: k + 1])
+    assert np.array_equal(pml[: k * 150].astype(np.uint32), want_p) and np.array_equal(cid[: k * 150], want_c)
