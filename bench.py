@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- query bases/s (PML + chain statistics) of the B200 path, next to the reference's CPU pml_query.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (backward move-structure traversal, PML + chain id per base) over one batch
+of synthetic reads.  Workload at every N: BASELINE.json configs[1] per GPU -- a synthetic 32-haplotype x 10 Mbp
+pangenome (+ reverse complements, 0.1 % SNP/indel divergence), marks = tunnels, sub-sample 10, and 10 M x 150 bp
+reads with 1 % substitutions -- index replicated per GPU, each rank traversing its own 10 M reads (weak scaling,
+no data-path collective).  Prints ONE JSON line (rank 0).
+
+Keys beyond the driver contract:
+  value     whole-job bases/s with reads + table resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       same metric through the C-ABI call colbwt_query with HOST (pinned) buffers: host 2-bit packing, H2D, traversal,
+            D2H of PML (u16) + CID (u8) all inside the timed region
+  roofline  the traversal kernel against the measured HBM stream peak (MEASURED_PEAKS.json), algorithmic bytes =
+            35.25 B/base (32 B gathered sector + 0.25 B read in + 3 B written); `gather` adds the
+            measured random-32-B-sector rate over a buffer of the index's size and the fraction of it achieved
+  cpu_baseline  the reference's own col_pml::query_pml (oracle/_ref, compiled from the reference sources) -- or the C
+            port when that is absent -- on the host cores, on a bounded sample of the same reads
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_BASE = 35.25   # SURVEY.md section 8d / DESIGN.md
+
+WORKLOADS = {
+    # name: (haplotypes, genome bp, snp, indel, reads, read_len, sub, ins, del, len_sigma, tree)
+    "c1": dict(H=4, G=1_000_000, snp=1e-3, indel=0.0, reads=100_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
+    "c2": dict(H=32, G=10_000_000, snp=9e-4, indel=1e-4, reads=10_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
+    "c2small": dict(H=32, G=1_000_000, snp=9e-4, indel=1e-4, reads=2_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
+    "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=100_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
+}
+WORKLOADS["tiny"] = dict(H=4, G=50_000, snp=1e-3, indel=0.0, reads=5_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False)
+WORKLOAD_TEXT = {
+    "tiny": "4-haplotype x 50 kbp toy (CPU self-test of bench.py only)",
+    "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
+    "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
+    "c2small": "configs[1] scaled down 10x in genome length and 5x in reads (smoke runs only)",
+    "c3small": "configs[2] scaled down 10x: 64-haplotype x 5 Mbp tree-structured pangenome, 100k x 10 kbp nanopore-like reads at 5% error",
+}
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed regions run."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.active = threading.Event()
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cache_dir():
+    d = os.environ.get("COLBWT_BENCH_CACHE", "/tmp/colbwt_bench_cache")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def build_workload(name: str, device: str, verbose: bool):
+    """Generates (or loads from the per-box cache) the index file and the text the reads are drawn from."""
+    from synthdata import pangenome as P, pipeline as PL
+    w = WORKLOADS[name]
+    stem = os.path.join(cache_dir(), name)
+    meta_path = stem + ".meta.json"
+    if not os.path.exists(meta_path):
+        t0 = time.time()
+        haps = P.make_haplotypes(w["G"], w["H"], snp=w["snp"], indel=w["indel"], seed=1, tree=w["tree"])
+        idx = PL.build_index(haps, with_revcomp=True, split_rate=10, min_mum=20, device=device, verbose=verbose)
+        PL.write_col_pml(stem + ".col_pml", idx["columns"])
+        np.save(stem + ".text.npy", idx["text"])
+        np.save(stem + ".seq_starts.npy", idx["seq_starts"])
+        cols = idx["columns"]
+        meta = {"n": int(cols["n"]), "r": int(cols["ch"].size), "bwt_r": int(cols["bwt_r"]), "mums": int(idx["mum_len"].size),
+                "marked_rows": int((cols["col_id"] > 0).sum()), "build_s": time.time() - t0}
+        with open(meta_path + ".tmp", "w") as f:
+            json.dump(meta, f)
+        os.replace(meta_path + ".tmp", meta_path)
+    meta = json.load(open(meta_path))
+    return stem + ".col_pml", np.load(stem + ".text.npy", mmap_mode="r"), np.load(stem + ".seq_starts.npy"), meta
+
+
+def make_reads(name: str, text, seq_starts, rank: int, n_reads: int | None, device: str):
+    from synthdata import pangenome as P
+    w = WORKLOADS[name]
+    n = n_reads or w["reads"]
+    return P.sample_reads_device(np.asarray(text), seq_starts, n, w["read_len"], sub=w["sub"], ins=w["ins"], dele=w["dele"],
+                                 len_sigma=w["len_sigma"], seed=2 + rank, device=device)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(workload: str):
+    """dram bytes per launch of the traversal kernel from the committed ncu capture of this workload, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+def cpu_reference(path: str):
+    """The CPU checker/baseline: the reference's own code if oracle/_ref travelled here, else the C port."""
+    import oracle
+    if oracle.have_ref():
+        return oracle.Reference(path), "reference"
+    return oracle.Oracle(path), "port"
+
+
+def time_cpu(ref, kind, seqs, off, threads, target_s):
+    """Reference on a bounded sample: calibrate on 2k reads, then size the sample for ~target_s seconds."""
+    n_reads = off.size - 1
+    k0 = min(n_reads, 2000)
+
+    def run(k):
+        o = off[: k + 1]
+        s = seqs[: int(o[-1])]
+        t0 = time.perf_counter()
+        if kind == "reference":
+            ref.query_batch(s, o, threads=threads, want_output=False)
+        else:
+            ref.query_batch(s, o, want_output=False)
+        return int(o[-1]), time.perf_counter() - t0
+    b0, t0 = run(k0)
+    rate = b0 / max(t0, 1e-6)
+    k = int(min(n_reads, max(k0, target_s * rate / max(1, b0 / k0))))
+    return k, run
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("COLBWT_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    have_gpu = torch.cuda.is_available()
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        return run_reference(a, have_gpu)
+
+    if not have_gpu:
+        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        return 1
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import col_bwt_b200 as cb
+    dev = f"cuda:{local}"
+    # rank 0 generates into the box-local cache, the others load it
+    if rank == 0:
+        path, text, seq_starts, meta = build_workload(a.workload, dev, a.verbose)
+    barrier()
+    if rank != 0:
+        path, text, seq_starts, meta = build_workload(a.workload, dev, a.verbose)
+    seqs, off = make_reads(a.workload, text, seq_starts, rank, a.reads, dev)
+    torch.cuda.empty_cache()
+    n_reads, n_bases = off.size - 1, int(off[-1])
+    max_len = int(np.diff(off).max())
+    width = cb.PML_U16 if max_len < 65536 else cb.PML_U32
+
+    tbl = cb.ColPml.load(path, devices=[local])
+    st = tbl.stats
+    batch = tbl.batch(seqs, off, width)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- kernel-only: reads + table resident in HBM ------------------------------------------------------------
+    for _ in range(a.warmup):
+        batch.run(1)
+    barrier()
+    sampler.active.set()
+    t0 = time.perf_counter()
+    ms_per_step = batch.run(a.steps)            # CUDA events around K back-to-back traversals on the launching stream
+    barrier()
+    wall_kernel = time.perf_counter() - t0
+    sampler.active.clear()
+    ms_per_step = max_over_ranks(ms_per_step)
+    value = world * n_bases / (ms_per_step * 1e-3)
+
+    # ---- parity spot check against the oracle (not timed; checker only) ------------------------------------------
+    pml_d, cid_d = batch.download()
+    k = min(n_reads, 2000)
+    ref, kind = cpu_reference(path)
+    want = ref.query_batch(seqs[: int(off[k])], off[: k + 1])
+    parity = bool(np.array_equal(pml_d[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(cid_d[: int(off[k])], want[1]))
+    mismatch_frac = float((pml_d[: min(n_bases, 50_000_000)] == 0).mean())
+    cid_frac = float((cid_d[: min(n_bases, 50_000_000)] > 0).mean())
+    del pml_d, cid_d
+
+    # ---- end to end through the C-ABI with host buffers ----------------------------------------------------------------
+    h_seqs = cb.PinnedArray(n_bases, np.uint8)
+    h_seqs.array[:] = seqs
+    h_pml = cb.PinnedArray(n_bases, np.uint16 if width == 2 else np.uint32)
+    h_cid = cb.PinnedArray(n_bases, np.uint8)
+    for _ in range(2):
+        tbl.query(h_seqs.array, off, width, out=(h_pml.array, h_cid.array))
+    barrier()
+    sampler.active.set()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        tbl.query(h_seqs.array, off, width, out=(h_pml.array, h_cid.array))
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
+    sampler.active.clear()
+    e2e_value = world * n_bases / e2e_s
+    e2e_parity = bool(np.array_equal(h_pml.array[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(h_cid.array[: int(off[k])], want[1]))
+    h2d = int(((np.diff(off).astype(np.int64) + 15) // 16).sum() * 4 + 16 * n_reads)
+    d2h = n_bases * (width + 1)
+    sampler.stop_flag.set()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline ----------------------------------------------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    per_gpu_bases_s = n_bases / (ms_per_step * 1e-3)
+    achieved = per_gpu_bases_s * ALGO_BYTES_PER_BASE / 1e9
+    table_bytes = int(st.r) * 16
+    s_rand = cb.gather_bench(max(table_bytes, 1 << 20), 1 << 28, False, local)
+    s_dep = cb.gather_bench(max(table_bytes, 1 << 20), 1 << 26, True, local)
+    roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": profiled_traffic(a.workload), "peak_source": peak_src, "kernel": "k_traverse<packed,u16>",
+                "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
+                "gather": {"table_bytes": table_bytes, "random_sector_rate_per_s": s_rand, "dependent_sector_rate_per_s": s_dep,
+                           "frac_of_random_sector_rate": round(per_gpu_bases_s / s_rand, 4)}}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------------------------
+    cpu = None
+    if world == 1 and a.cpu_seconds > 0:
+        cores = os.cpu_count() or 1
+        threads = cores if kind == "reference" else 1
+        kk, run = time_cpu(ref, kind, seqs, off, threads, a.cpu_seconds)
+        b, t = run(kk)
+        cpu = {"value": b / t, "unit": "bases/s", "cores": threads, "kind": kind,
+               "sample": f"first {kk} reads ({b} bases) of the same batch, {t:.2f} s; MULTI_THREAD off (output-identical, SURVEY.md 6)"}
+
+    out = {
+        "metric": "query bases/sec (PML + chain stats)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32/u16/u8 integer", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[a.workload], "name": a.workload, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
+                   "index": {"n": int(st.n), "rows": int(st.r), "bwt_runs": int(st.bwt_r), "marked_rows": int(st.marked_rows),
+                             "exact_search_rows": int(st.slow_rows), "hbm_bytes": int(st.device_bytes)},
+                   "parallelism": f"index replicated x{world}, reads sharded, no collective",
+                   "l2": "no flush needed: table + per-step outputs exceed the 126 MB L2" if table_bytes + d2h > (200 << 20) else "working set fits L2 (small workload)",
+                   "mismatch_step_frac": round(mismatch_frac, 4), "cid_nonzero_frac": round(cid_frac, 4)},
+        "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s,
+                "api": "colbwt_query (host pinned buffers; host 2-bit packing inside the timed region)"},
+        "gpu_launches": batch.launches * a.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind},
+        "wall_s_kernel_region": wall_kernel,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if (parity and e2e_parity) else 2
+
+
+def run_reference(a, have_gpu):
+    """--impl reference: the reference's own CPU implementation on this box's host cores, same workload/metric."""
+    dev = "cuda:0" if have_gpu else "cpu"
+    path, text, seq_starts, meta = build_workload(a.workload, dev, a.verbose)
+    # a bounded sample of the same reads (rank 0's batch); enough for the calibration to size the steps
+    cap = min(a.reads or WORKLOADS[a.workload]["reads"], 400_000 if WORKLOADS[a.workload]["read_len"] < 1000 else 6000)
+    seqs, off = make_reads(a.workload, text, seq_starts, 0, cap, dev)
+    ref, kind = cpu_reference(path)
+    cores = os.cpu_count() or 1
+    threads = cores if kind == "reference" else 1
+    kk, run = time_cpu(ref, kind, seqs, off, threads, max(2.0, a.cpu_seconds))
+    for _ in range(a.warmup):
+        run(max(1, kk // 4))
+    times, bases = [], 0
+    for _ in range(a.steps):
+        b, t = run(kk)
+        bases = b
+        times.append(t)
+    s_per_step = float(np.mean(times))
+    v = bases / s_per_step
+    out = {
+        "impl": "reference", "metric": "query bases/sec (PML + chain stats)", "value": v, "unit": "bases/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 integer (CPU)", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[a.workload], "name": a.workload, "reads_per_step": kk, "bases_per_step": bases},
+        "cpu_baseline": {"value": v, "unit": "bases/s", "cores": threads, "kind": kind,
+                         "sample": f"{kk} reads ({bases} bases) of the workload per step; col_pml::query_pml on {threads} host threads sharing one table; MULTI_THREAD off (output-identical)"},
+        "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
