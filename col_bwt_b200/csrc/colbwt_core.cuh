@@ -84,16 +84,59 @@ constexpr uint32_t BUILD_FLAG_BAD_LEN = 1u;   // row of length 0 or >= 65536
 constexpr uint32_t BUILD_FLAG_SLOW = 2u;      // some (row, character) needs the exact search
 constexpr uint32_t BUILD_FLAG_BAD_LF = 4u;    // dest >= r
 
+// L2 residency policy handles (createpolicy): the table is kept (evict_last), everything streamed once -- packed
+// reads in, PML/CID out -- is marked evict_first so that it does not push table lines out of the 126 MB L2.
+struct Policies {
+    uint64_t keep = 0, stream = 0;
+};
+
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-CB_HD Row ld_row(const Row *p)
+__device__ __forceinline__ Policies make_policies()
 {
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    Policies p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+    return p;
+}
+template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &pol)
+{
+    uint4 v;
+    if (HINTS)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol.keep));
+    else
+        v = __ldg(reinterpret_cast<const uint4 *>(p));
     return Row{v.x, v.y, v.z, v.w};
 }
 template <typename T> CB_HD T ld_ro(const T *p) { return __ldg(p); }
+template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &pol)
+{
+    if (!HINTS) return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol.stream));
+    return v;
+}
+template <int HINTS> CB_HD void st_stream_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Policies &pol)
+{
+    if (HINTS)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol.stream) : "memory");
+    else
+        *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
+}
+template <int HINTS> CB_HD void st_stream_v2(void *p, uint32_t a, uint32_t b, const Policies &pol)
+{
+    if (HINTS)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol.stream) : "memory");
+    else
+        *reinterpret_cast<uint2 *>(p) = make_uint2(a, b);
+}
 #else
-CB_HD Row ld_row(const Row *p) { return *p; }
+CB_HD Policies make_policies() { return Policies{}; }
+template <int HINTS> CB_HD void st_stream_v4(void *, uint32_t, uint32_t, uint32_t, uint32_t, const Policies &) {}
+template <int HINTS> CB_HD void st_stream_v2(void *, uint32_t, uint32_t, const Policies &) {}
+template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &) { return *p; }
 template <typename T> CB_HD T ld_ro(const T *p) { return *p; }
+template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &) { return *p; }
 #endif
 
 // Build the packed row k from the reference columns.  Pure function of the columns.
@@ -219,14 +262,14 @@ template <typename PmlT> struct Lane {
     uint32_t accc[2] = {0, 0};         // 8 staged CID bytes
 };
 
-template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g)
+template <int HINTS, typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g, const Policies &pol)
 {
     uint8_t *cid = bv.cid + g;
     if (L.cnt == 8) {   // aligned full group: g % 8 == 0
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-        *reinterpret_cast<uint2 *>(cid) = make_uint2(L.accc[0], L.accc[1]);
+        st_stream_v2<HINTS>(cid, L.accc[0], L.accc[1], pol);
         if (sizeof(PmlT) == 2)
-            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(bv.pml) + g) = make_uint4(L.accp[0], L.accp[1], L.accp[2], L.accp[3]);
+            st_stream_v4<HINTS>(reinterpret_cast<uint16_t *>(bv.pml) + g, L.accp[0], L.accp[1], L.accp[2], L.accp[3], pol);
 #else
         for (int t = 0; t < 8; ++t) cid[t] = (uint8_t)(L.accc[t >> 2] >> (8 * (t & 3)));
         if (sizeof(PmlT) == 2)
@@ -251,7 +294,7 @@ template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &b
     L.cnt = 0;
 }
 
-template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)
+template <int HINTS, typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid, const Policies &pol)
 {
     const uint64_t g = L.out_base + jj;
     L.accc[1] = (L.accc[1] << 8) | (L.accc[0] >> 24);
@@ -265,11 +308,12 @@ template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv
         reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
     }
     ++L.cnt;
-    if ((g & 7) == 0 || jj == 0) lane_flush(L, bv, g);
+    if ((g & 7) == 0 || jj == 0) lane_flush<HINTS>(L, bv, g, pol);
 }
 
 // Start read `m` on this lane (zero-length reads are skipped by the caller).
-template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ReadMeta &m)
+template <bool PACKED, int HINTS, typename PmlT>
+CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ReadMeta &m, const Policies &pol)
 {
     L.state = LANE_LF;
     L.addr = t.r - 1;               // col_bwt.hpp:504
@@ -279,12 +323,12 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const
     L.in_off = m.in_off;
     L.out_base = m.out_off;
     L.cnt = 0;
-    if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
+    if (PACKED) L.rw = ld_stream_u32<HINTS>(bv.words + m.in_off + ((m.len - 1) >> 4), pol);
 }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
-template <bool PACKED, typename PmlT>
-CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
+template <bool PACKED, int HINTS, typename PmlT>
+CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut, const Policies &pol)
 {
     const uint32_t len = row_len(row);
     if (L.state != LANE_LF) {
@@ -306,7 +350,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     uint8_t cbyte = 0;
     if (PACKED) {
         code = (L.rw >> (2 * (jj & 15))) & 3u;
-        if ((jj & 15) == 0 && jj != 0) L.rw = ld_ro(bv.words + L.in_off + ((jj - 1) >> 4));
+        if ((jj & 15) == 0 && jj != 0) L.rw = ld_stream_u32<HINTS>(bv.words + L.in_off + ((jj - 1) >> 4), pol);
     } else {
         cbyte = ld_ro(bv.bytes + L.in_off + jj);
         code = code_lut[cbyte];
@@ -321,7 +365,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     } else {
         L.plen = 0;                              // col_bwt.hpp:520-523
     }
-    lane_emit(L, bv, jj, L.plen, cid);
+    lane_emit<HINTS>(L, bv, jj, L.plen, cid, pol);
     if (jj == 0) {                               // the reference's last LF step has no observable effect
         L.state = LANE_IDLE;
         return;

@@ -16,8 +16,8 @@ namespace colbwt {
 
 constexpr int TRAVERSE_THREADS = 256;
 
-template <bool PACKED, typename PmlT>
-__global__ void __launch_bounds__(TRAVERSE_THREADS, 2048 / TRAVERSE_THREADS)
+template <bool PACKED, typename PmlT, int HINTS, int CTAS>
+__global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
     __shared__ uint8_t code_lut[256];
@@ -28,6 +28,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     const uint32_t lane = threadIdx.x & 31;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const uint32_t count = PACKED ? bv.n_packed : bv.n_bytes;
+    const Policies pol = HINTS ? make_policies() : Policies{};
     Lane<PmlT> L;
     bool exhausted = false;
     for (;;) {
@@ -46,7 +47,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
                     m.out_off = (uint64_t)mv.x | ((uint64_t)mv.y << 32);
                     m.len = mv.z;
                     m.in_off = mv.w;
-                    if (m.len) lane_begin<PACKED>(L, t, bv, m);   // zero-length read: nothing to emit
+                    if (m.len) lane_begin<PACKED, HINTS>(L, t, bv, m, pol);   // zero-length read: nothing to emit
                 } else {
                     exhausted = true;
                 }
@@ -55,34 +56,73 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
         if (__all_sync(0xffffffffu, exhausted && L.state == LANE_IDLE)) break;
         // ---- one gather per active lane ------------------------------------------------------------------------
         if (L.state != LANE_IDLE) {
-            const Row row = ld_row(t.rows + L.addr);
-            lane_step<PACKED>(L, t, bv, row, code_lut);
+            const Row row = ld_row<HINTS>(t.rows + L.addr, pol);
+            lane_step<PACKED, HINTS>(L, t, bv, row, code_lut, pol);
         }
     }
+}
+
+template <bool PACKED, typename PmlT>
+static void launch_variant(int variant, unsigned grid_per_cta8, int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv,
+                           const uint8_t *lut, unsigned long long *cursor, cudaStream_t stream)
+{
+    (void)grid_per_cta8;
+    auto grid_for = [&](int ctas) {
+        const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
+        return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
+    };
+    static const int ctas = getenv("COLBWT_CTAS") ? atoi(getenv("COLBWT_CTAS")) : 6;
+    const int hints = variant & 1;
+#define CB_LAUNCH(H, C) k_traverse<PACKED, PmlT, H, C><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor)
+    if (hints) {
+        switch (ctas) {
+        case 2: CB_LAUNCH(1, 2); break;
+        case 3: CB_LAUNCH(1, 3); break;
+        case 4: CB_LAUNCH(1, 4); break;
+        case 5: CB_LAUNCH(1, 5); break;
+        case 8: CB_LAUNCH(1, 8); break;
+        default: CB_LAUNCH(1, 6); break;
+        }
+    } else {
+        switch (ctas) {
+        case 2: CB_LAUNCH(0, 2); break;
+        case 3: CB_LAUNCH(0, 3); break;
+        case 4: CB_LAUNCH(0, 4); break;
+        case 5: CB_LAUNCH(0, 5); break;
+        case 8: CB_LAUNCH(0, 8); break;
+        default: CB_LAUNCH(0, 6); break;
+        }
+    }
+#undef CB_LAUNCH
 }
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)
 {
     // two cursors: [0] packed reads, [1] byte reads
     CB_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned long long), stream));
-    const int ctas_per_sm = 2048 / TRAVERSE_THREADS;
+    static const int variant = getenv("COLBWT_VARIANT") ? atoi(getenv("COLBWT_VARIANT")) : 0;
+    if (variant & 4) {   // bit 2: persisting-L2 access window over the packed rows
+        cudaDeviceProp prop;
+        CB_CUDA(cudaGetDeviceProperties(&prop, dt.device));
+        CB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+        cudaStreamAttrValue attr{};
+        const size_t bytes = std::min<size_t>((size_t)dt.view.r * sizeof(Row), (size_t)prop.accessPolicyMaxWindowSize);
+        attr.accessPolicyWindow.base_ptr = const_cast<Row *>(dt.view.rows);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)prop.persistingL2CacheMaxSize / (double)bytes));
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CB_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     const uint8_t *lut = (const uint8_t *)dt.d_code_lut;
-    auto grid_for = [&](uint32_t reads) {
-        const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
-        return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)dt.sm_count * ctas_per_sm));
-    };
     if (bv.n_packed) {
-        if (pml_width == 2)
-            k_traverse<true, uint16_t><<<grid_for(bv.n_packed), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, d_cursors);
-        else
-            k_traverse<true, uint32_t><<<grid_for(bv.n_packed), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, d_cursors);
+        if (pml_width == 2) launch_variant<true, uint16_t>(variant, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else launch_variant<true, uint32_t>(variant, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         CB_CUDA(cudaGetLastError());
     }
     if (bv.n_bytes) {
-        if (pml_width == 2)
-            k_traverse<false, uint16_t><<<grid_for(bv.n_bytes), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, d_cursors + 1);
-        else
-            k_traverse<false, uint32_t><<<grid_for(bv.n_bytes), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, d_cursors + 1);
+        if (pml_width == 2) launch_variant<false, uint16_t>(variant, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else launch_variant<false, uint32_t>(variant, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         CB_CUDA(cudaGetLastError());
     }
     return COLBWT_OK;
@@ -101,7 +141,23 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     return x;
 }
 
-template <bool DEPENDENT>
+// Load flavours under test (the row gather of k_traverse uses the winner, see ld_row in colbwt_core.cuh).
+template <int V> __device__ __forceinline__ uint4 ld_variant(const uint4 *p)
+{
+    uint4 v;
+    if (V == 0) return __ldg(p);                 // ld.global.nc
+    else if (V == 1) return __ldcg(p);           // ld.global.cg  (L2 only)
+    else if (V == 2) return __ldcs(p);           // ld.global.cs  (streaming)
+    else if (V == 3) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (V == 4) return __ldcv(p);           // ld.global.cv
+    else if (V == 5) asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (V == 6) return __ldlu(p);           // ld.global.lu
+    else if (V == 7) asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else v = *p;                                  // ld.global (default .ca)
+    return v;
+}
+
+template <bool DEPENDENT, int V>
 __global__ void __launch_bounds__(256, 8)
 k_gather_bench(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t loads_per_thread, uint32_t *sink)
 {
@@ -110,19 +166,34 @@ k_gather_bench(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t loads
     uint32_t acc = 0;
     if (DEPENDENT) {
         for (uint32_t i = 0; i < loads_per_thread; ++i) {
-            const uint4 v = __ldg(buf + 2 * (s % n_sectors));      // one 16-byte half of a random 32-byte sector
+            const uint4 v = ld_variant<V>(buf + 2 * (s % n_sectors));   // one 16-byte half of a random 32-byte sector
             acc ^= v.y;
-            s = mix64(s + v.x);                                     // next address depends on the loaded value
+            s = mix64(s + v.x);                                          // next address depends on the loaded value
         }
     } else {
 #pragma unroll 8
         for (uint32_t i = 0; i < loads_per_thread; ++i) {
-            const uint4 v = __ldg(buf + 2 * (s % n_sectors));
+            const uint4 v = ld_variant<V>(buf + 2 * (s % n_sectors));
             acc ^= v.x ^ v.y;
             s = mix64(s + i);
         }
     }
     if (acc == 0x12345678u) sink[0] = acc;
+}
+
+template <bool DEP> static void launch_gather(int variant, unsigned grid, const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint32_t *sink)
+{
+    switch (variant) {
+    case 1: k_gather_bench<DEP, 1><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 2: k_gather_bench<DEP, 2><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 3: k_gather_bench<DEP, 3><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 4: k_gather_bench<DEP, 4><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 5: k_gather_bench<DEP, 5><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 6: k_gather_bench<DEP, 6><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 7: k_gather_bench<DEP, 7><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 8: k_gather_bench<DEP, 8><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    default: k_gather_bench<DEP, 0><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    }
 }
 
 __global__ void k_fill(uint4 *buf, uint64_t n)
@@ -145,6 +216,7 @@ extern "C" int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, i
     CB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     CB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (const char *e = getenv("COLBWT_L2_FETCH")) CB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
     const uint64_t n_sectors = bytes / 32;
     uint4 *buf = nullptr;
     uint32_t *sink = nullptr;
@@ -160,8 +232,8 @@ extern "C" int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, i
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {   // first repetition is the warm-up
         CB_CUDA(cudaEventRecord(e0));
-        if (dependent) k_gather_bench<true><<<grid, 256>>>(buf, n_sectors, per_thread, sink);
-        else k_gather_bench<false><<<grid, 256>>>(buf, n_sectors, per_thread, sink);
+        if (dependent & 1) launch_gather<true>(dependent >> 8, grid, buf, n_sectors, per_thread, sink);
+        else launch_gather<false>(dependent >> 8, grid, buf, n_sectors, per_thread, sink);
         CB_CUDA(cudaEventRecord(e1));
         CB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

@@ -113,8 +113,8 @@ size_t colbwt_format_stats(char *buf, size_t cap, const char *id, size_t id_len,
 /* ---- measurement helpers ------------------------------------------------------------------------------- */
 
 /* Random-gather roofline microbenchmark on `device`: `loads` independent 16-byte loads, each from a random
- * 32-byte sector of a `bytes`-sized buffer.  dependent != 0 chains each thread's next address on the loaded
- * value (latency-bound variant with the same occupancy).  *sectors_per_s receives the measured rate. */
+ * 32-byte sector of a `bytes`-sized buffer.  bit 0 of `dependent` chains each thread's next address on the loaded
+ * value (latency-bound variant with the same occupancy); bits 8.. select the load flavour under test (0 = ld.global.nc).  *sectors_per_s receives the measured rate. */
 int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, int dependent, double *sectors_per_s);
 
 const char *colbwt_last_error(void);

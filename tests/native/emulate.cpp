@@ -84,9 +84,10 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
         ReadMeta m{off[i], (uint32_t)len, packed ? 0u : (uint32_t)off[i]};
         auto run = [&](auto &L, auto packed_tag) {
             constexpr bool P = decltype(packed_tag)::value;
-            lane_begin<P>(L, t->view, bv, m);
+            Policies pol;
+            lane_begin<P, 0>(L, t->view, bv, m, pol);
             while (L.state != LANE_IDLE) {
-                lane_step<P>(L, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                lane_step<P, 0>(L, t->view, bv, ld_row<0>(t->view.rows + L.addr, pol), t->code_lut, pol);
                 ++iters;
             }
         };
