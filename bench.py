@@ -13,7 +13,7 @@ no data-path collective).  Prints ONE JSON line (rank 0).
 Keys beyond the driver contract:
   value     whole-job bases/s with reads + table resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e       same metric through the C-ABI call colbwt_query with HOST (pinned) buffers: host 2-bit packing, H2D, traversal,
-            D2H of PML (u16) + CID (u8) all inside the timed region
+            D2H of PML (u8 for reads < 256 bases, else u16/u32) + CID (u8) all inside the timed region
   roofline  the traversal kernel against the measured HBM stream peak (MEASURED_PEAKS.json), algorithmic bytes =
             35.25 B/base (32 B gathered sector + 0.25 B read in + 3 B written); `gather` adds the
             measured random-32-B-sector rate over a buffer of the index's size and the fraction of it achieved
@@ -34,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES_PER_BASE = 35.25   # SURVEY.md section 8d / DESIGN.md
+ALGO_BYTES_PER_BASE = 35.25   # SURVEY.md section 8d / DESIGN.md (32 B gathered + 0.25 B in + 3 B out; kept fixed even when PML is written as u8)
 
 WORKLOADS = {
     # name: (haplotypes, genome bp, snp, indel, reads, read_len, sub, ins, del, len_sigma, tree)
@@ -243,7 +243,8 @@ def main():
     torch.cuda.empty_cache()
     n_reads, n_bases = off.size - 1, int(off[-1])
     max_len = int(np.diff(off).max())
-    width = cb.PML_U16 if max_len < 65536 else cb.PML_U32
+    width = cb.PML_U8 if max_len < 256 else (cb.PML_U16 if max_len < 65536 else cb.PML_U32)
+    pml_dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width]
 
     tbl = cb.ColPml.load(path, devices=[local])
     st = tbl.stats
@@ -277,7 +278,7 @@ def main():
     # ---- end to end through the C-ABI with host buffers ----------------------------------------------------------------
     h_seqs = cb.PinnedArray(n_bases, np.uint8)
     h_seqs.array[:] = seqs
-    h_pml = cb.PinnedArray(n_bases, np.uint16 if width == 2 else np.uint32)
+    h_pml = cb.PinnedArray(n_bases, pml_dtype)
     h_cid = cb.PinnedArray(n_bases, np.uint8)
     for _ in range(2):
         tbl.query(h_seqs.array, off, width, out=(h_pml.array, h_cid.array))
@@ -308,7 +309,7 @@ def main():
     s_rand = cb.gather_bench(max(table_bytes, 1 << 20), 1 << 28, False, local)
     s_dep = cb.gather_bench(max(table_bytes, 1 << 20), 1 << 26, True, local)
     roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": profiled_traffic(a.workload), "peak_source": peak_src, "kernel": "k_traverse<packed,u16>",
+                "traffic": profiled_traffic(a.workload), "peak_source": peak_src, "kernel": f"k_traverse<packed,u{8 * width}>",
                 "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
                 "gather": {"table_bytes": table_bytes, "random_sector_rate_per_s": s_rand, "dependent_sector_rate_per_s": s_dep,
                            "frac_of_random_sector_rate": round(per_gpu_bases_s / s_rand, 4)}}
@@ -334,7 +335,7 @@ def main():
                    "l2": "no flush needed: table + per-step outputs exceed the 126 MB L2" if table_bytes + d2h > (200 << 20) else "working set fits L2 (small workload)",
                    "mismatch_step_frac": round(mismatch_frac, 4), "cid_nonzero_frac": round(cid_frac, 4)},
         "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s,
-                "api": "colbwt_query (host pinned buffers; host 2-bit packing inside the timed region)"},
+                "pml_bytes": width, "api": "colbwt_query (host pinned buffers; host 2-bit packing inside the timed region)"},
         "gpu_launches": batch.launches * a.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind},

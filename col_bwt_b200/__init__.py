@@ -67,7 +67,8 @@ for _name, (_res, _args) in EXPORTS.items():
     _f.restype = _res
     _f.argtypes = _args
 
-PML_U16, PML_U32 = 2, 4
+PML_U8, PML_U16, PML_U32 = 1, 2, 4
+_PML_DTYPE = {1: np.uint8, 2: np.uint16, 4: np.uint32}
 
 
 def version() -> str:
@@ -138,7 +139,7 @@ class Batch:
         return _L.colbwt_batch_launches(self._h)
 
     def download(self):
-        pml = np.zeros(self.n_bases, np.uint16 if self.pml_width == 2 else np.uint32)
+        pml = np.zeros(self.n_bases, _PML_DTYPE[self.pml_width])
         cid = np.zeros(self.n_bases, np.uint8)
         _check(_L.colbwt_batch_download(self._h, pml.ctypes.data, cid.ctypes.data), "colbwt_batch_download")
         return pml, cid
@@ -201,7 +202,7 @@ class ColPml:
         seqs, offsets = _as_batch(seqs, offsets)
         total = int(offsets[-1] - offsets[0])
         if out is None:
-            pml = np.zeros(total, np.uint16 if pml_width == 2 else np.uint32)
+            pml = np.zeros(total, _PML_DTYPE[pml_width])
             cid = np.zeros(total, np.uint8)
         else:
             pml, cid = out

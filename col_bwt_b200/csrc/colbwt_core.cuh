@@ -56,9 +56,26 @@ CB_HD uint32_t row_cid(const Row &r) { return r.m0 & 0xFFu; }
 CB_HD uint32_t row_chc(const Row &r) { return (r.m0 >> 8) & 7u; }
 CB_HD uint64_t row_meta(const Row &r) { return (uint64_t)r.m0 | ((uint64_t)r.m1 << 32); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Narrow layout: the same row split into two 8-byte words so that the array every step gathers from is half as
+// large (twice the L2 reach; an L2 miss on this machine always costs a full 128-byte line).
+//   hot  = dest:32 | doff:10 | len:10 | chc:3 | cid:8      (every step)
+//   cold = mode:3x2 | dist:3x10 | fx:16                    (= wide meta >> 11; only after a mismatch)
+// Usable when every row is shorter than 1024 symbols.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t NARROW_MAX_LEN = 1023;
+CB_HD uint64_t hot_from_row(const Row &r)
+{
+    return (uint64_t)r.dest | ((uint64_t)(row_doff(r) & 1023u) << 32) | ((uint64_t)(row_len(r) & 1023u) << 42) |
+           ((uint64_t)row_chc(r) << 52) | ((uint64_t)row_cid(r) << 55);
+}
+CB_HD uint64_t cold_from_row(const Row &r) { return row_meta(r) >> 11; }
+
 // Device-resident table (all pointers in HBM).
 struct TableView {
-    const Row *rows;            // r packed rows
+    const Row *rows;            // r packed rows (wide layout)
+    const uint64_t *hot;        // narrow layout: dest/doff/len/chc/cid per row (nullptr when not built)
+    const uint64_t *cold;       // narrow layout: reposition modes/distances/flip offset per row
     const uint8_t *ch8;         // r exact row bytes                      (slow path, "other" characters)
     const uint64_t *idx;        // r BWT start positions                  (slow path: pos = idx[k]+offset)
     const uint64_t *thr;        // r thresholds                           (slow path)
@@ -109,6 +126,13 @@ template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &pol)
     return Row{v.x, v.y, v.z, v.w};
 }
 template <typename T> CB_HD T ld_ro(const T *p) { return __ldg(p); }
+template <int HINTS> CB_HD uint64_t ld_row64(const uint64_t *p, const Policies &pol)
+{
+    if (!HINTS) return __ldg(reinterpret_cast<const unsigned long long *>(p));
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol.keep));
+    return v;
+}
 template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &pol)
 {
     if (!HINTS) return __ldg(p);
@@ -118,6 +142,7 @@ template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Polic
 }
 template <int HINTS> CB_HD void st_stream_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Policies &pol)
 {
+    if (HINTS == 2) return;   // experiment: no output traffic
     if (HINTS)
         asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol.stream) : "memory");
     else
@@ -125,6 +150,7 @@ template <int HINTS> CB_HD void st_stream_v4(void *p, uint32_t a, uint32_t b, ui
 }
 template <int HINTS> CB_HD void st_stream_v2(void *p, uint32_t a, uint32_t b, const Policies &pol)
 {
+    if (HINTS == 2) return;
     if (HINTS)
         asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol.stream) : "memory");
     else
@@ -135,6 +161,7 @@ CB_HD Policies make_policies() { return Policies{}; }
 template <int HINTS> CB_HD void st_stream_v4(void *, uint32_t, uint32_t, uint32_t, uint32_t, const Policies &) {}
 template <int HINTS> CB_HD void st_stream_v2(void *, uint32_t, uint32_t, const Policies &) {}
 template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &) { return *p; }
+template <int HINTS> CB_HD uint64_t ld_row64(const uint64_t *p, const Policies &) { return *p; }
 template <typename T> CB_HD T ld_ro(const T *p) { return *p; }
 template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &) { return *p; }
 #endif
@@ -243,7 +270,9 @@ struct BatchView {
     uint32_t n_packed, n_bytes;
 };
 
-enum LaneState : uint32_t { LANE_IDLE = 0, LANE_LF = 1, LANE_REPOS_SUCC = 2, LANE_REPOS_PRED = 3 };
+enum LaneState : uint32_t { LANE_IDLE = 0, LANE_LF = 1, LANE_REPOS_SUCC = 2, LANE_REPOS_PRED = 3,
+                            LANE_COLD = 4 /* narrow: gather cold[addr]; read code in bits 8-9, row chc in bits 10-11 */,
+                            LANE_RELOAD = 5 /* narrow: nothing found, gather hot[addr] again and LF through it */ };
 
 // Per-lane registers.  Every iteration of the traversal loop performs exactly one row gather per lane
 // (`rows[addr]`) whatever the lane needs next -- LF destination, fast-forward neighbour or reposition target --
@@ -258,7 +287,7 @@ template <typename PmlT> struct Lane {
     uint32_t rw = 0;        // current packed word
     uint64_t out_base = 0;
     uint32_t cnt = 0;       // staged outputs
-    uint32_t accp[4] = {0, 0, 0, 0};   // 8 staged u16 PML values (lowest position in the low bits)
+    uint32_t accp[4] = {0, 0, 0, 0};   // 8 staged u16 (or u8) PML values, lowest position in the low bits
     uint32_t accc[2] = {0, 0};         // 8 staged CID bytes
 };
 
@@ -270,10 +299,14 @@ template <int HINTS, typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const B
         st_stream_v2<HINTS>(cid, L.accc[0], L.accc[1], pol);
         if (sizeof(PmlT) == 2)
             st_stream_v4<HINTS>(reinterpret_cast<uint16_t *>(bv.pml) + g, L.accp[0], L.accp[1], L.accp[2], L.accp[3], pol);
+        else if (sizeof(PmlT) == 1)
+            st_stream_v2<HINTS>(reinterpret_cast<uint8_t *>(bv.pml) + g, L.accp[0], L.accp[1], pol);
 #else
         for (int t = 0; t < 8; ++t) cid[t] = (uint8_t)(L.accc[t >> 2] >> (8 * (t & 3)));
         if (sizeof(PmlT) == 2)
             for (int t = 0; t < 8; ++t) reinterpret_cast<uint16_t *>(bv.pml)[g + t] = (uint16_t)(L.accp[t >> 1] >> (16 * (t & 1)));
+        else if (sizeof(PmlT) == 1)
+            for (int t = 0; t < 8; ++t) reinterpret_cast<uint8_t *>(bv.pml)[g + t] = (uint8_t)(L.accp[t >> 2] >> (8 * (t & 3)));
 #endif
     } else {
         uint32_t c0 = L.accc[0], c1 = L.accc[1];
@@ -288,6 +321,10 @@ template <int HINTS, typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const B
                 p1 = (p1 >> 16) | (p2 << 16);
                 p2 = (p2 >> 16) | (p3 << 16);
                 p3 >>= 16;
+            } else if (sizeof(PmlT) == 1) {
+                reinterpret_cast<uint8_t *>(bv.pml)[g + t] = (uint8_t)p0;
+                p0 = (p0 >> 8) | (p1 << 24);
+                p1 >>= 8;
             }
         }
     }
@@ -304,6 +341,9 @@ template <int HINTS, typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const Ba
         L.accp[2] = (L.accp[2] << 16) | (L.accp[1] >> 16);
         L.accp[1] = (L.accp[1] << 16) | (L.accp[0] >> 16);
         L.accp[0] = (L.accp[0] << 16) | (plen & 0xFFFFu);
+    } else if (sizeof(PmlT) == 1) {
+        L.accp[1] = (L.accp[1] << 8) | (L.accp[0] >> 24);
+        L.accp[0] = (L.accp[0] << 8) | (plen & 0xFFu);
     } else {
         reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
     }
@@ -398,6 +438,93 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     }
     L.off = row_doff(row) + L.off;               // LF_table.hpp:253-254
     L.addr = row.dest;
+}
+
+
+// Narrow-layout twin of lane_step.  `w` = hot[addr], or cold[addr] when the lane is in LANE_COLD.
+template <bool PACKED, int HINTS, typename PmlT>
+CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut,
+                            const Policies &pol)
+{
+    const uint32_t st = L.state & 7u;
+    if (st == LANE_COLD) {
+        const uint32_t code = (L.state >> 8) & 3u, rchc = (L.state >> 10) & 3u;
+        const uint32_t slot = (code - rchc - 1u) & 3u;
+        const uint32_t mode = (uint32_t)(w >> (2 * slot)) & 3u;
+        bool found, use_pred = false;
+        uint32_t tgt = 0;
+        if (mode == 3) {
+            found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+        } else {
+            const uint32_t d = (uint32_t)(w >> (6 + 10 * slot)) & 1023u;
+            const uint32_t fx = (uint32_t)(w >> 36) & 0xFFFFu;
+            use_pred = (mode == 1) || (mode == 2 && L.off < fx);
+            tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
+            found = true;
+        }
+        if (found) {
+            L.addr = tgt;
+            L.state = use_pred ? LANE_REPOS_PRED : LANE_REPOS_SUCC;
+        } else {
+            L.state = LANE_RELOAD;
+        }
+        return;
+    }
+    const uint32_t dest = (uint32_t)w;
+    const uint32_t doff = (uint32_t)(w >> 32) & 1023u;
+    const uint32_t len = (uint32_t)(w >> 42) & 1023u;
+    const uint32_t chc = (uint32_t)(w >> 52) & 7u;
+    const uint32_t cid = (uint32_t)(w >> 55) & 255u;
+    if (st != LANE_LF) {
+        uint32_t o = L.off;                                   // LANE_RELOAD: keep the offset
+        if (st == LANE_REPOS_PRED) o = len - 1;
+        else if (st == LANE_REPOS_SUCC) o = 0;
+        L.off = doff + o;
+        L.addr = dest;
+        L.state = LANE_LF;
+        return;
+    }
+    if (L.off >= len && L.addr + 1 < t.r) {
+        L.off -= len;
+        ++L.addr;
+        return;
+    }
+    const uint32_t jj = --L.j;
+    uint32_t code;
+    uint8_t cbyte = 0;
+    if (PACKED) {
+        code = (L.rw >> (2 * (jj & 15))) & 3u;
+        if ((jj & 15) == 0 && jj != 0) L.rw = ld_stream_u32<HINTS>(bv.words + L.in_off + ((jj - 1) >> 4), pol);
+    } else {
+        cbyte = ld_ro(bv.bytes + L.in_off + jj);
+        code = code_lut[cbyte];
+    }
+    bool match = (code == chc);
+    if (!PACKED && code >= CODE_OTHER)
+        match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
+    L.plen = match ? L.plen + 1 : 0;
+    lane_emit<HINTS>(L, bv, jj, L.plen, cid, pol);
+    if (jj == 0) {
+        L.state = LANE_IDLE;
+        return;
+    }
+    if (!match) {
+        if ((PACKED || code < CODE_OTHER) && chc != CHC_OTHER) {
+            L.state = LANE_COLD | (code << 8) | (chc << 10);   // next trip gathers cold[addr]
+            return;
+        }
+        bool found = false, use_pred = false;
+        uint32_t tgt = 0;
+        if (PACKED || code < CODE_OTHER) found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+        else if (code == CODE_OTHER) found = slow_reposition(t, L.addr, L.off, cbyte, &tgt, &use_pred);
+        if (found) {
+            L.addr = tgt;
+            L.state = use_pred ? LANE_REPOS_PRED : LANE_REPOS_SUCC;
+            return;
+        }
+    }
+    L.off = doff + L.off;
+    L.addr = dest;
 }
 
 } // namespace colbwt

@@ -59,6 +59,15 @@ __global__ void k_build_rows(BuildView b, Row *rows, unsigned long long *counter
     }
 }
 
+__global__ void k_narrow_rows(const Row *__restrict__ rows, uint64_t r, uint64_t *hot, uint64_t *cold)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= r) return;
+    const Row row = rows[k];
+    hot[k] = hot_from_row(row);
+    cold[k] = cold_from_row(row);
+}
+
 __global__ void k_iota(uint32_t *v, uint64_t n)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,6 +91,8 @@ void free_device_table(DeviceTable &dt)
     if (dt.device < 0) return;
     cudaSetDevice(dt.device);
     cudaFree(dt.d_rows);
+    cudaFree(dt.d_hot);
+    cudaFree(dt.d_cold);
     cudaFree(dt.d_ch8);
     cudaFree(dt.d_idx);
     cudaFree(dt.d_thr);
@@ -225,6 +236,16 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
     CB_CUDA(cudaMemcpy(&last_idx, (const uint64_t *)dt.d_idx + (r - 1), 8, cudaMemcpyDeviceToHost));
     CB_CUDA(cudaDeviceSynchronize());
 
+    // narrow layout (half-size gather array) when every row is short enough
+    if (h_counters[3] <= NARROW_MAX_LEN && !(getenv("COLBWT_NARROW") && atoi(getenv("COLBWT_NARROW")) == 0)) {
+        CB_CUDA(cudaMalloc(&dt.d_hot, r * 8));
+        CB_CUDA(cudaMalloc(&dt.d_cold, r * 8));
+        k_narrow_rows<<<(unsigned)((r + 255) / 256), 256>>>((const Row *)dt.d_rows, r, (uint64_t *)dt.d_hot, (uint64_t *)dt.d_cold);
+        CB_CUDA(cudaGetLastError());
+        CB_CUDA(cudaDeviceSynchronize());
+    }
+    dt.view.hot = (const uint64_t *)dt.d_hot;
+    dt.view.cold = (const uint64_t *)dt.d_cold;
     dt.view.rows = (const Row *)dt.d_rows;
     dt.view.ch8 = (const uint8_t *)dt.d_ch8;
     dt.view.idx = (const uint64_t *)dt.d_idx;
@@ -234,7 +255,7 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
     dt.view.n = n;
     dt.view.r = (uint32_t)r;
     dt.view.last_len = (uint32_t)(n - last_idx);
-    dt.bytes = r * (sizeof(Row) + 1 + 8 + 8 + 4) + sizeof(h_start) + 256;
+    dt.bytes = r * (sizeof(Row) + (dt.d_hot ? 16 : 0) + 1 + 8 + 8 + 4) + sizeof(h_start) + 256;
     if (stats) {
         stats->marked_rows = h_counters[1];
         stats->slow_rows = h_counters[2];

@@ -29,7 +29,7 @@ void set_error(const char *fmt, ...);
 struct DeviceTable {
     int device = -1;
     TableView view{};
-    void *d_rows = nullptr, *d_ch8 = nullptr, *d_idx = nullptr, *d_thr = nullptr, *d_char_rows = nullptr,
+    void *d_rows = nullptr, *d_hot = nullptr, *d_cold = nullptr, *d_ch8 = nullptr, *d_idx = nullptr, *d_thr = nullptr, *d_char_rows = nullptr,
          *d_char_start = nullptr, *d_code_lut = nullptr;
     uint64_t bytes = 0;
     int sm_count = 0;
@@ -59,6 +59,10 @@ void free_device_table(DeviceTable &dt);
 // Packs reads [r0, r1) of a batch: 2-bit words at word offsets word_off[i] (relative to words),
 // returns false for reads that contain a byte outside ACGT (their words are garbage, caller ships bytes).
 bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
+// Packs reads [r0, r1) of a batch (one thread's slice): metas at meta[i - r_base], words from word index w on;
+// seq_end = number of readable bytes in seqs (bounds the 32-byte over-reads); irregular read numbers go to irr.
+void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t r_base, uint64_t base0,
+                uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr);
 
 // kernels (index.cu / traverse.cu) launched through these host wrappers
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_counters,

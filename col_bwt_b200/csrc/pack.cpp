@@ -6,6 +6,9 @@
 // "irregular": it is shipped as raw bytes and traversed by the byte kernel, so comparisons stay byte-exact.
 #include <cstdint>
 #include <cstring>
+#include <vector>
+
+#include "colbwt_core.cuh"
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -74,6 +77,80 @@ static bool pack_scalar(const uint8_t *seq, uint64_t len, uint32_t *words)
         words[w] = v;
     }
     return ok;
+}
+
+#if defined(__x86_64__)
+// Slice packer: reads [r0, r1), words written from word index `w` on, metas at meta[i - r_base].  Reads whose bytes
+// are followed by >= 32 more readable bytes use whole 32-byte loads (the bytes past the read are masked out of the
+// validity test and only the read's own words are stored).  Irregular reads are appended to `irr`.
+__attribute__((target("avx2"))) static void pack_slice_avx2(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1,
+                                                          uint64_t r_base, uint64_t base0, uint64_t seq_end, uint32_t *words,
+                                                          uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr)
+{
+    for (uint64_t i = r0; i < r1; ++i) {
+        const uint64_t beg = off[i], len = off[i + 1] - beg;
+        ReadMeta m{beg - base0, (uint32_t)len, (uint32_t)w};
+        bool ok = true;
+        if (len) {
+            const uint8_t *p = seqs + beg;
+            uint32_t *out = words + w;
+            if (beg + ((len + 31) & ~31ull) <= seq_end) {
+                uint64_t j = 0;
+                for (; j + 32 <= len; j += 32) {
+                    uint64_t v;
+                    ok &= pack32_avx2(p + j, &v);
+                    memcpy(out + (j >> 4), &v, 8);
+                }
+                if (j < len) {   // tail: over-read, judge only the read's own bytes
+                    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + j));
+                    const __m256i code = _mm256_and_si256(_mm256_srli_epi16(x, 1), _mm256_set1_epi8(3));
+                    const __m256i lut = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                                         'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+                    const uint32_t good = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, code), x));
+                    const uint32_t need = (uint32_t)((1ull << (len - j)) - 1);
+                    ok &= (good & need) == need;
+                    const __m256i n4 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));
+                    const __m256i n8 = _mm256_madd_epi16(n4, _mm256_set1_epi32(0x00100001));
+                    const __m256i sh = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                        0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+                    const __m256i g = _mm256_shuffle_epi8(n8, sh);
+                    out[j >> 4] = (uint32_t)_mm256_extract_epi32(g, 0);
+                    if (len - j > 16) out[(j >> 4) + 1] = (uint32_t)_mm256_extract_epi32(g, 4);
+                }
+            } else {
+                ok = pack_avx2(p, len, out);
+            }
+        }
+        if (!ok) {
+            m.len = 0;   // skipped by the packed kernel, shipped as bytes
+            irr.push_back(i);
+        }
+        meta[i - r_base] = m;
+        w += (len + 15) >> 4;
+    }
+}
+#endif
+
+void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t r_base, uint64_t base0,
+                uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr)
+{
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        pack_slice_avx2(seqs, off, r0, r1, r_base, base0, seq_end, words, w, meta, irr);
+        return;
+    }
+#endif
+    for (uint64_t i = r0; i < r1; ++i) {
+        const uint64_t len = off[i + 1] - off[i];
+        ReadMeta m{off[i] - base0, (uint32_t)len, (uint32_t)w};
+        if (len && !pack_scalar(seqs + off[i], len, words + w)) {
+            m.len = 0;
+            irr.push_back(i);
+        }
+        meta[i - r_base] = m;
+        w += (len + 15) >> 4;
+    }
 }
 
 bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words)

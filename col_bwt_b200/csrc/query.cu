@@ -8,6 +8,7 @@
 // No inter-GPU communication exists on this path.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -120,7 +121,7 @@ static inline uint64_t words_of(uint64_t len) { return (len + 15) >> 4; }
 
 // Reads [r0, r1) of (seqs, off).  Output offsets are relative to off[r0].  Staging arrays must hold
 // (r1-r0) metas (x2), sum(words_of(len)) words and up to n_bases bytes.
-static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, Staging &st)
+static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t seq_end, Staging &st)
 {
     Pool &pool = Pool::get();
     const uint64_t n_reads = r1 - r0, base0 = off[r0], n_bases = off[r1] - base0;
@@ -152,20 +153,7 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
     // pass B: pack; remember irregular reads per slice
     std::vector<std::vector<uint64_t>> irr(T);
     pool.parallel_for(T, [&](int t) {
-        uint64_t w = wcount[t];
-        for (uint64_t i = cut[t]; i < cut[t + 1]; ++i) {
-            const uint64_t len = off[i + 1] - off[i];
-            ReadMeta m;
-            m.out_off = off[i] - base0;
-            m.len = (uint32_t)len;
-            m.in_off = (uint32_t)w;
-            if (len && !pack_read_2bit(seqs + off[i], len, st.words + w)) {
-                m.len = 0;   // skipped by the packed kernel
-                irr[t].push_back(i);
-            }
-            st.meta[i - r0] = m;
-            w += words_of(len);
-        }
+        pack_slice(seqs, off, cut[t], cut[t + 1], r0, base0, seq_end, st.words, wcount[t], st.meta, irr[t]);
         uint64_t b = 0;
         for (uint64_t i : irr[t]) b += off[i + 1] - off[i];
         icount[t + 1] = irr[t].size();
@@ -211,8 +199,12 @@ struct colbwt_batch {
 
 static int check_width(int pml_width, uint32_t max_len)
 {
-    if (pml_width != COLBWT_PML_U16 && pml_width != COLBWT_PML_U32) {
-        set_error("pml_width must be 2 or 4");
+    if (pml_width != COLBWT_PML_U8 && pml_width != COLBWT_PML_U16 && pml_width != COLBWT_PML_U32) {
+        set_error("pml_width must be 1, 2 or 4");
+        return COLBWT_ERR_ARG;
+    }
+    if (pml_width == COLBWT_PML_U8 && max_len > 255) {
+        set_error("a read of %u bases does not fit 8-bit PML values; use COLBWT_PML_U16", max_len);
         return COLBWT_ERR_ARG;
     }
     if (pml_width == COLBWT_PML_U16 && max_len > 65535) {
@@ -273,7 +265,7 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     st.meta_b = meta_b.data();
     st.words = words.data();
     st.bytes = bytes.data();
-    prepare_reads(seqs, off, 0, n_reads, st);
+    prepare_reads(seqs, off, 0, n_reads, off[n_reads], st);
     if (int rc = check_width(pml_width, st.max_len)) return rc;
     if (st.n_byte_bases >= (1ull << 32)) {
         set_error("colbwt_batch_upload: more than 4 Gi bases of irregular reads in one batch; split it");
@@ -374,6 +366,7 @@ struct Slot {
     unsigned long long *d_cursors = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};   // COLBWT_TRACE=2: H2D start / kernel start / D2H start / end
     // pending copy-out when the caller's buffers are not pinned
     bool pending = false;
     uint64_t out_base = 0, out_bases = 0;
@@ -403,6 +396,7 @@ struct Pipeline {
             cudaFree(k.d_cid);
             cudaFree(k.d_cursors);
             if (k.done) cudaEventDestroy(k.done);
+            for (auto e : k.tev) if (e) cudaEventDestroy(e);
             if (k.stream) cudaStreamDestroy(k.stream);
         }
     }
@@ -456,6 +450,7 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
         CB_CUDA(cudaMalloc(&k.d_cursors, 2 * sizeof(unsigned long long)));
         CB_CUDA(cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking));
         CB_CUDA(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+        for (auto &e : k.tev) CB_CUDA(cudaEventCreate(&e));
     }
     idx->pipeline = pl.release();
     *out = idx->pipeline;
@@ -490,10 +485,27 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     Pipeline &pl = *plp;
     const bool staged_out = !(is_pinned(pml) && is_pinned(cid));
 
+    static const int trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
+    struct ChunkTimes { float h2d0, k0, d2h0, end; };
+    std::vector<ChunkTimes> timeline;
+    cudaEvent_t ev_origin = nullptr;
+    if (trace >= 2) {
+        CB_CUDA(cudaSetDevice(idx->dev[0].device));
+        CB_CUDA(cudaEventCreate(&ev_origin));
+        CB_CUDA(cudaEventRecord(ev_origin, pl.slots[0].stream));
+    }
     uint8_t *pml_out = (uint8_t *)pml;
     auto drain = [&](Slot &k) -> int {   // wait for the slot's previous chunk; copy out if staged
         if (!k.pending) return COLBWT_OK;
         CB_CUDA(cudaEventSynchronize(k.done));
+        if (trace >= 2) {
+            ChunkTimes ct{};
+            cudaEventElapsedTime(&ct.h2d0, ev_origin, k.tev[0]);
+            cudaEventElapsedTime(&ct.k0, ev_origin, k.tev[1]);
+            cudaEventElapsedTime(&ct.d2h0, ev_origin, k.tev[2]);
+            cudaEventElapsedTime(&ct.end, ev_origin, k.tev[3]);
+            timeline.push_back(ct);
+        }
         if (staged_out) {
             memcpy(pml_out + k.out_base * (uint64_t)pml_width, k.h_out, k.out_bases * (uint64_t)pml_width);
             memcpy(cid + k.out_base, k.h_out + pl.cap_bases * (uint64_t)pml_width + 32, k.out_bases);
@@ -502,6 +514,9 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         return COLBWT_OK;
     };
 
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_pack = 0, t_drain = 0, t_enqueue = 0;
+    const double t_begin = now();
     uint64_t r0 = 0, chunk_no = 0;
     while (r0 < n_reads) {
         // next chunk [r0, r1): at most chunk_bases bases and chunk_reads reads, at least one read
@@ -512,15 +527,21 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         Slot &k = pl.slots[(size_t)d * SLOTS_PER_DEVICE + (size_t)((chunk_no / (uint64_t)n_dev) % SLOTS_PER_DEVICE)];
         const DeviceTable &dt = idx->dev[d];
         CB_CUDA(cudaSetDevice(dt.device));
+        double t0 = now();
         if (int rc = drain(k)) return rc;
+        t_drain += now() - t0;
+        t0 = now();
 
         Staging st;
         st.meta = k.h_meta;
         st.meta_b = k.h_meta_b;
         st.words = k.h_words;
         st.bytes = k.h_bytes;
-        prepare_reads(seqs, off, r0, r1, st);
+        prepare_reads(seqs, off, r0, r1, off[n_reads], st);
+        t_pack += now() - t0;
+        t0 = now();
 
+        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[0], k.stream));
         CB_CUDA(cudaMemcpyAsync(k.d_meta, k.h_meta, st.n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
         CB_CUDA(cudaMemcpyAsync(k.d_words, k.h_words, st.n_words * 4, cudaMemcpyHostToDevice, k.stream));
         if (st.n_irregular) {
@@ -536,7 +557,9 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         bv.cid = k.d_cid;
         bv.n_packed = (uint32_t)st.n_reads;
         bv.n_bytes = (uint32_t)st.n_irregular;
+        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[1], k.stream));
         if (int rc = launch_traverse(dt, bv, pml_width, k.d_cursors, k.stream)) return rc;
+        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
         const uint64_t ob = off[r0] - off[0];
         if (staged_out) {
             CB_CUDA(cudaMemcpyAsync(k.h_out, k.d_pml, st.n_bases * (uint64_t)pml_width, cudaMemcpyDeviceToHost, k.stream));
@@ -545,17 +568,33 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
             CB_CUDA(cudaMemcpyAsync(pml_out + ob * (uint64_t)pml_width, k.d_pml, st.n_bases * (uint64_t)pml_width, cudaMemcpyDeviceToHost, k.stream));
             CB_CUDA(cudaMemcpyAsync(cid + ob, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
         }
+        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
         CB_CUDA(cudaEventRecord(k.done, k.stream));
         k.pending = true;
         k.out_base = ob;
         k.out_bases = st.n_bases;
         r0 = r1;
         ++chunk_no;
+        t_enqueue += now() - t0;
     }
+    const double t_loop = now() - t_begin;
     for (size_t s = 0; s < pl.slots.size(); ++s) {
         CB_CUDA(cudaSetDevice(idx->dev[s / SLOTS_PER_DEVICE].device));
         if (int rc = drain(pl.slots[s])) return rc;
     }
+    if (trace >= 2 && n_dev == 1) {
+        float h2d = 0, ker = 0, d2h = 0;
+        for (auto &c : timeline) { h2d += c.k0 - c.h2d0; ker += c.d2h0 - c.k0; d2h += c.end - c.d2h0; }
+        fprintf(stderr, "[colbwt_query] stream time per stage, summed over chunks: H2D %.1f ms, kernel %.1f ms, D2H %.1f ms; last chunk ends at %.1f ms\n",
+                h2d, ker, d2h, timeline.empty() ? 0.f : timeline.back().end);
+        for (size_t i = 0; i < timeline.size(); i += std::max<size_t>(1, timeline.size() / 8))
+            fprintf(stderr, "    chunk %3zu: H2D %.2f..%.2f kernel ..%.2f D2H ..%.2f ms\n", i, timeline[i].h2d0, timeline[i].k0, timeline[i].d2h0, timeline[i].end);
+    }
+    if (ev_origin) cudaEventDestroy(ev_origin);
+    if (trace)
+        fprintf(stderr, "[colbwt_query] %llu chunks, %.1f Mbases: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, loop %.1f ms, total %.1f ms (%s outputs)\n",
+                (unsigned long long)chunk_no, total_bases / 1e6, t_pack * 1e3, t_drain * 1e3, t_enqueue * 1e3, t_loop * 1e3,
+                (now() - t_begin) * 1e3, staged_out ? "staged" : "pinned");
     return COLBWT_OK;
 }
 

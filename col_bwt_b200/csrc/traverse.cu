@@ -16,7 +16,7 @@ namespace colbwt {
 
 constexpr int TRAVERSE_THREADS = 256;
 
-template <bool PACKED, typename PmlT, int HINTS, int CTAS>
+template <bool PACKED, typename PmlT, int HINTS, int CTAS, bool NARROW>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
@@ -28,7 +28,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     const uint32_t lane = threadIdx.x & 31;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const uint32_t count = PACKED ? bv.n_packed : bv.n_bytes;
-    const Policies pol = HINTS ? make_policies() : Policies{};
+    const Policies pol = HINTS == 1 ? make_policies() : Policies{};
     Lane<PmlT> L;
     bool exhausted = false;
     for (;;) {
@@ -56,8 +56,14 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
         if (__all_sync(0xffffffffu, exhausted && L.state == LANE_IDLE)) break;
         // ---- one gather per active lane ------------------------------------------------------------------------
         if (L.state != LANE_IDLE) {
-            const Row row = ld_row<HINTS>(t.rows + L.addr, pol);
-            lane_step<PACKED, HINTS>(L, t, bv, row, code_lut, pol);
+            if (NARROW) {
+                const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
+                const uint64_t w = ld_row64<HINTS>(base + L.addr, pol);
+                lane_step_narrow<PACKED, HINTS>(L, t, bv, w, code_lut, pol);
+            } else {
+                const Row row = ld_row<HINTS>(t.rows + L.addr, pol);
+                lane_step<PACKED, HINTS>(L, t, bv, row, code_lut, pol);
+            }
         }
     }
 }
@@ -71,27 +77,24 @@ static void launch_variant(int variant, unsigned grid_per_cta8, int sm_count, ui
         const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
         return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
     };
-    static const int ctas = getenv("COLBWT_CTAS") ? atoi(getenv("COLBWT_CTAS")) : 6;
-    const int hints = variant & 1;
-#define CB_LAUNCH(H, C) k_traverse<PACKED, PmlT, H, C><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor)
-    if (hints) {
-        switch (ctas) {
-        case 2: CB_LAUNCH(1, 2); break;
-        case 3: CB_LAUNCH(1, 3); break;
-        case 4: CB_LAUNCH(1, 4); break;
-        case 5: CB_LAUNCH(1, 5); break;
-        case 8: CB_LAUNCH(1, 8); break;
-        default: CB_LAUNCH(1, 6); break;
-        }
-    } else {
-        switch (ctas) {
-        case 2: CB_LAUNCH(0, 2); break;
-        case 3: CB_LAUNCH(0, 3); break;
-        case 4: CB_LAUNCH(0, 4); break;
-        case 5: CB_LAUNCH(0, 5); break;
-        case 8: CB_LAUNCH(0, 8); break;
-        default: CB_LAUNCH(0, 6); break;
-        }
+    static const int ctas = getenv("COLBWT_CTAS") ? atoi(getenv("COLBWT_CTAS")) : 4;
+    static const int narrow_env = getenv("COLBWT_NARROW") ? atoi(getenv("COLBWT_NARROW")) : 1;
+    const bool narrow = dt.view.hot != nullptr && narrow_env != 0;
+    (void)variant;
+    static const bool nostore = getenv("COLBWT_NOSTORE") != nullptr;   // experiment only: results are not written
+#define CB_LAUNCH(C)                                                                                                        \
+    do {                                                                                                                    \
+        if (nostore) k_traverse<PACKED, PmlT, 2, C, true><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);  \
+        else if (narrow) k_traverse<PACKED, PmlT, 0, C, true><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);  \
+        else k_traverse<PACKED, PmlT, 0, C, false><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);        \
+    } while (0)
+    switch (ctas) {
+    case 2: CB_LAUNCH(2); break;
+    case 3: CB_LAUNCH(3); break;
+    case 5: CB_LAUNCH(5); break;
+    case 6: CB_LAUNCH(6); break;
+    case 8: CB_LAUNCH(8); break;
+    default: CB_LAUNCH(4); break;
     }
 #undef CB_LAUNCH
 }
@@ -100,29 +103,17 @@ int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, u
 {
     // two cursors: [0] packed reads, [1] byte reads
     CB_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned long long), stream));
-    static const int variant = getenv("COLBWT_VARIANT") ? atoi(getenv("COLBWT_VARIANT")) : 0;
-    if (variant & 4) {   // bit 2: persisting-L2 access window over the packed rows
-        cudaDeviceProp prop;
-        CB_CUDA(cudaGetDeviceProperties(&prop, dt.device));
-        CB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
-        cudaStreamAttrValue attr{};
-        const size_t bytes = std::min<size_t>((size_t)dt.view.r * sizeof(Row), (size_t)prop.accessPolicyMaxWindowSize);
-        attr.accessPolicyWindow.base_ptr = const_cast<Row *>(dt.view.rows);
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)prop.persistingL2CacheMaxSize / (double)bytes));
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        CB_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    }
     const uint8_t *lut = (const uint8_t *)dt.d_code_lut;
     if (bv.n_packed) {
-        if (pml_width == 2) launch_variant<true, uint16_t>(variant, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
-        else launch_variant<true, uint32_t>(variant, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        if (pml_width == 2) launch_variant<true, uint16_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else if (pml_width == 1) launch_variant<true, uint8_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else launch_variant<true, uint32_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         CB_CUDA(cudaGetLastError());
     }
     if (bv.n_bytes) {
-        if (pml_width == 2) launch_variant<false, uint16_t>(variant, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
-        else launch_variant<false, uint32_t>(variant, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        if (pml_width == 2) launch_variant<false, uint16_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else if (pml_width == 1) launch_variant<false, uint8_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else launch_variant<false, uint32_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         CB_CUDA(cudaGetLastError());
     }
     return COLBWT_OK;

@@ -58,7 +58,9 @@ typedef struct colbwt_stats {
     int32_t  n_devices;
 } colbwt_stats;
 
-/* Width in bytes of one PML value in caller buffers: 2 (reads shorter than 65536) or 4. */
+/* Width in bytes of one PML value in caller buffers: 1 (every read shorter than 256 bases), 2 (shorter than
+ * 65536) or 4.  A PML never exceeds the read length, so the narrow widths lose nothing; they cut the D2H bytes. */
+#define COLBWT_PML_U8 1
 #define COLBWT_PML_U16 2
 #define COLBWT_PML_U32 4
 

@@ -57,11 +57,11 @@ class Emu:
         self.L.emu_rows(self.h, out.ctypes.data)
         return out
 
-    def query(self, seqs, offsets, pml_width=2, force_bytes=False):
+    def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False):
         seqs = np.ascontiguousarray(seqs, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
-        pml = np.zeros(seqs.size + 8, np.uint16 if pml_width == 2 else np.uint32)
+        pml = np.zeros(seqs.size + 8, {1: np.uint8, 2: np.uint16, 4: np.uint32}[pml_width])
         cid = np.zeros(seqs.size + 8, np.uint8)
         self.iters = self.L.emu_query(self.h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data,
-                                      pml_width, cid.ctypes.data, int(force_bytes))
+                                      pml_width, cid.ctypes.data, int(force_bytes) | (2 if narrow else 0))
         return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]

@@ -21,13 +21,14 @@ def cols_from_file(path):
 @pytest.mark.parametrize("case", ["toy", "pan4"])
 @pytest.mark.parametrize("width", [2, 4])
 @pytest.mark.parametrize("force_bytes", [False, True])
-def test_emulated_kernel_logic_on_golden(golden_dir, case, width, force_bytes):
+@pytest.mark.parametrize("narrow", [False, True])
+def test_emulated_kernel_logic_on_golden(golden_dir, case, width, force_bytes, narrow):
     path = os.path.join(golden_dir, f"{case}.col_pml")
     orc = oracle.Oracle(path)
     emu = Emu(cols_from_file(path))
     ids, seqs, off = parse_fastx(os.path.join(golden_dir, f"{case}_reads.fa"))
     p0, c0 = orc.query_batch(seqs, off)
-    p1, c1 = emu.query(seqs, off, pml_width=width, force_bytes=force_bytes)
+    p1, c1 = emu.query(seqs, off, pml_width=width, force_bytes=force_bytes, narrow=narrow)
     assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
 
 
@@ -39,9 +40,14 @@ def test_emulated_kernel_logic_on_synthetic(small_index):
     for seqs, off in ((small_index["seqs"], small_index["off"]), (extra, eoff)):
         p0, c0 = orc.query_batch(seqs, off)
         for fb in (False, True):
-            p1, c1 = emu.query(seqs, off, force_bytes=fb)
-            assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+            for narrow in (False, True):
+                p1, c1 = emu.query(seqs, off, force_bytes=fb, narrow=narrow)
+                assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
         check_pml_properties(p1, off)
+    # 8-bit PML: legal when every read is shorter than 256 bases
+    p0, c0 = orc.query_batch(small_index["seqs"], small_index["off"])
+    p1, c1 = emu.query(small_index["seqs"], small_index["off"], pml_width=1)
+    assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
@@ -62,8 +68,9 @@ def test_emulated_random_tables_small_alphabet_quirks(seed):
     extra, eoff = concat_reads(adversarial_reads(haps))
     for s, o in ((seqs, off), (extra, eoff)):
         p0, c0 = orc.query_batch(s, o)
-        p1, c1 = emu.query(s, o)
-        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+        for narrow in (False, True):
+            p1, c1 = emu.query(s, o, narrow=narrow)
+            assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
 
 
 def test_far_reposition_targets_take_exact_search():
@@ -80,8 +87,9 @@ def test_far_reposition_targets_take_exact_search():
     reads = [bytes(a[100:200]) + b"G" + bytes(a[300:330]), b"GGGG" + bytes(a[5:50]) + b"T", bytes(b[10:90])]
     s, o = concat_reads(reads)
     p0, c0 = orc.query_batch(s, o)
-    p1, c1 = emu.query(s, o)
-    assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+    for narrow in (False, True):
+        p1, c1 = emu.query(s, o, narrow=narrow)
+        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
 
 
 def test_row_builder_flags_overlong_rows():
@@ -116,3 +124,37 @@ def test_host_packer_matches_scalar_definition():
                 t = s.copy()
                 t[pos] = bad[0]
                 assert L.emu_pack(t.ctypes.data, n, w.ctypes.data) == 0
+
+
+def test_slice_packer_overreads_safely_and_flags_irregular_reads():
+    import ctypes as C
+    from emu import SO, build
+    build()
+    L = C.CDLL(SO)
+    L.emu_pack_slice.restype = C.c_uint64
+    L.emu_pack_slice.argtypes = [C.c_void_p] * 2 + [C.c_uint64] + [C.c_void_p] * 3
+    rng = np.random.default_rng(1)
+    lens = [150, 1, 0, 16, 17, 31, 32, 33, 64, 149, 3, 150, 150, 7]      # the last reads sit at the very end of the buffer
+    reads = [bytes(P.ACGT[rng.integers(0, 4, n)]) for n in lens]
+    reads[4] = reads[4][:5] + b"N" + reads[4][6:]
+    reads[9] = reads[9][:-1] + b"a"                                        # irregular in the last byte
+    reads[12] = b"n" + reads[12][1:]
+    # the byte right AFTER a regular read being irregular must not make that read irregular (over-read masking)
+    reads[1] = b"C"
+    seqs, off = concat_reads(reads)
+    seqs = np.concatenate((seqs, np.zeros(0, np.uint8)))
+    n = len(reads)
+    words = np.zeros(int(((np.diff(off).astype(np.int64) + 15) // 16).sum()) + 4, np.uint32)
+    meta = np.zeros(4 * n, np.uint64)
+    irr = np.zeros(n, np.uint64)
+    k = L.emu_pack_slice(seqs.ctypes.data, off.ctypes.data, n, words.ctypes.data, meta.ctypes.data, irr.ctypes.data)
+    assert sorted(irr[:k].tolist()) == [4, 9, 12]
+    meta = meta.reshape(n, 4)
+    w = 0
+    for i, r in enumerate(reads):
+        assert meta[i, 0] == off[i] and meta[i, 2] == w
+        assert meta[i, 1] == (0 if i in (4, 9, 12) else len(r))
+        if i not in (4, 9, 12):
+            for j, c in enumerate(r):
+                assert (int(words[w + (j >> 4)]) >> (2 * (j & 15))) & 3 == (c >> 1) & 3
+        w += (len(r) + 15) // 16

@@ -52,7 +52,8 @@ def test_synthetic_index_vs_oracle_all_paths(cb, small_index):
     extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
     for seqs, off in ((small_index["seqs"], small_index["off"]), (extra, eoff)):
         want_p, want_c = orc.query_batch(seqs, off)
-        for width in (cb.PML_U16, cb.PML_U32):
+        widths = (cb.PML_U8, cb.PML_U16, cb.PML_U32) if int(np.diff(off).max()) < 256 else (cb.PML_U16, cb.PML_U32)
+        for width in widths:
             pml, cid = tbl.query(seqs, off, width)
             assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
             b = tbl.batch(seqs, off, width)
@@ -110,9 +111,10 @@ def test_variable_lengths_and_long_reads_u32(cb, small_index):
     tbl = cb.ColPml.load(small_index["path"])
     pml, cid = tbl.query(seqs, off, cb.PML_U32)
     assert np.array_equal(pml, want_p) and np.array_equal(cid, want_c)
-    with pytest.raises(cb.ColBwtError) as e:
-        tbl.query(seqs, off, cb.PML_U16)
-    assert e.value.code == -5
+    for too_narrow in (cb.PML_U16, cb.PML_U8):
+        with pytest.raises(cb.ColBwtError) as e:
+            tbl.query(seqs, off, too_narrow)
+        assert e.value.code == -5
 
 
 def test_nanopore_like_reads_with_indels(cb, small_index):

@@ -12,15 +12,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     b = tbl.batch(seqs, off)
     for _ in range(3): b.run(1)
     ms = b.run(5)
-    print(json.dumps({"variant": os.environ.get("COLBWT_VARIANT", "0"), "ctas": os.environ.get("COLBWT_CTAS", ""), "ms": ms, "gbases_s": seqs.size / ms / 1e6}))
+    print(json.dumps({"narrow": os.environ.get("COLBWT_NARROW", ""), "ctas": os.environ.get("COLBWT_CTAS", ""), "ms": ms, "gbases_s": seqs.size / ms / 1e6}))
 else:
     wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
     variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "2", "3", "4", "5", "7"]
     for v in variants:
         env = dict(os.environ)
-        if ":" in v:
-            env["COLBWT_VARIANT"], env["COLBWT_CTAS"] = v.split(":")
-        else:
-            env["COLBWT_VARIANT"] = v
+        env["COLBWT_NARROW"], env["COLBWT_CTAS"] = v.split(":")
         r = subprocess.run([sys.executable, __file__, "child", wl] + sys.argv[3:], env=env, capture_output=True, text=True)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-500:], flush=True)
