@@ -41,7 +41,7 @@ WORKLOADS = {
     "c1": dict(H=4, G=1_000_000, snp=1e-3, indel=0.0, reads=100_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
     "c2": dict(H=32, G=10_000_000, snp=9e-4, indel=1e-4, reads=10_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
     "c2small": dict(H=32, G=1_000_000, snp=9e-4, indel=1e-4, reads=2_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
-    "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=100_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
+    "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=400_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
 }
 WORKLOADS["tiny"] = dict(H=4, G=50_000, snp=1e-3, indel=0.0, reads=5_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False)
 WORKLOAD_TEXT = {
@@ -49,7 +49,7 @@ WORKLOAD_TEXT = {
     "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
     "c2small": "configs[1] scaled down 10x in genome length and 5x in reads (smoke runs only)",
-    "c3small": "configs[2] scaled down 10x: 64-haplotype x 5 Mbp tree-structured pangenome, 100k x 10 kbp nanopore-like reads at 5% error",
+    "c3small": "configs[2] scaled down: 64-haplotype x 5 Mbp tree-structured pangenome, 400k x 10 kbp (log-normal lengths) nanopore-like reads at 5% error",
 }
 
 
@@ -217,6 +217,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("COLBWT_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

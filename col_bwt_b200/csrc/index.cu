@@ -236,8 +236,10 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
     CB_CUDA(cudaMemcpy(&last_idx, (const uint64_t *)dt.d_idx + (r - 1), 8, cudaMemcpyDeviceToHost));
     CB_CUDA(cudaDeviceSynchronize());
 
-    // narrow layout (half-size gather array) when every row is short enough
-    if (h_counters[3] <= NARROW_MAX_LEN && !(getenv("COLBWT_NARROW") && atoi(getenv("COLBWT_NARROW")) == 0)) {
+    // Narrow layout (half-size gather array), opt-in with COLBWT_NARROW=1 when every row is short enough.  Measured on
+    // C2 it gains 4 % (DRAM lines per base 0.91 -> 0.87: the L2 keeps few random lines either way) and it costs one more
+    // dependent gather per mismatch, which lengthens the serial chain of long noisy reads; see DESIGN.md section 4.
+    if (h_counters[3] <= NARROW_MAX_LEN && getenv("COLBWT_NARROW") && atoi(getenv("COLBWT_NARROW")) == 1) {
         CB_CUDA(cudaMalloc(&dt.d_hot, r * 8));
         CB_CUDA(cudaMalloc(&dt.d_cold, r * 8));
         k_narrow_rows<<<(unsigned)((r + 255) / 256), 256>>>((const Row *)dt.d_rows, r, (uint64_t *)dt.d_hot, (uint64_t *)dt.d_cold);

@@ -115,6 +115,7 @@ struct Staging {
     uint8_t *bytes = nullptr;
     uint64_t n_reads = 0, n_words = 0, n_irregular = 0, n_byte_bases = 0, n_bases = 0;
     uint32_t max_len = 0;
+    bool sorted = false;
 };
 
 static inline uint64_t words_of(uint64_t len) { return (len + 15) >> 4; }
@@ -165,6 +166,12 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
     }
     st.n_irregular = icount[T];
     st.n_byte_bases = ibases[T];
+    // Lanes take reads in meta order (global cursor): with reads of very different lengths, start the longest first so
+    // that the last lanes to finish are working on short reads, not on a 100 kbp one.
+    if (st.max_len >= 1024 && n_reads > 1 && (uint64_t)st.max_len * n_reads > 2 * n_bases) {
+        std::sort(st.meta, st.meta + n_reads, [](const ReadMeta &a, const ReadMeta &b) { return a.len > b.len; });
+        st.sorted = true;
+    }
     if (st.n_irregular) {
         pool.parallel_for(T, [&](int t) {
             uint64_t k = icount[t], b = ibases[t];
@@ -352,7 +359,9 @@ extern "C" int colbwt_batch_device_ptrs(colbwt_batch *b, void **pml_dev, void **
 // ---------------------------------------------------------------------------------------------------------
 namespace colbwt {
 
-constexpr int SLOTS_PER_DEVICE = 3;
+// Chunks in flight per device.  One chunk's H2D -> kernel -> D2H chain takes ~3x its D2H time, so fewer than ~6 slots
+// leaves the D2H copy engine (the end-to-end bottleneck: 2-3 bytes out per base over PCIe) idle between chunks.
+static const int SLOTS_PER_DEVICE = getenv("COLBWT_SLOTS") ? std::max(1, std::min(16, atoi(getenv("COLBWT_SLOTS")))) : 6;
 
 struct Slot {
     // pinned host staging
@@ -469,14 +478,15 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     if (n_reads == 0) return COLBWT_OK;
     const uint64_t total_bases = off[n_reads] - off[0];
     // chunk geometry
-    uint64_t chunk_bases = 48ull << 20, chunk_reads = 4ull << 20;
+    uint64_t chunk_bases = 48ull << 20;
     if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     uint32_t max_len = 0;
     for (uint64_t i = 0; i < n_reads; ++i) max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
     if (int rc = check_width(pml_width, max_len)) return rc;
     chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
     chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
-    chunk_reads = std::min<uint64_t>(chunk_reads, n_reads);
+    // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
+    const uint64_t chunk_reads = std::min<uint64_t>(std::max<uint64_t>(chunk_bases / 32, 1024), n_reads);
 
     const int n_dev = (int)idx->dev.size();
     std::lock_guard<std::mutex> guard(idx->query_mutex);

@@ -78,8 +78,7 @@ static void launch_variant(int variant, unsigned grid_per_cta8, int sm_count, ui
         return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
     };
     static const int ctas = getenv("COLBWT_CTAS") ? atoi(getenv("COLBWT_CTAS")) : 4;
-    static const int narrow_env = getenv("COLBWT_NARROW") ? atoi(getenv("COLBWT_NARROW")) : 1;
-    const bool narrow = dt.view.hot != nullptr && narrow_env != 0;
+    const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
     (void)variant;
     static const bool nostore = getenv("COLBWT_NOSTORE") != nullptr;   // experiment only: results are not written
 #define CB_LAUNCH(C)                                                                                                        \

@@ -230,3 +230,33 @@ def test_config1_scale_properties_and_oracle_sample(cb, tmp_path):
     k = 20000
     want_p, want_c = oracle.Oracle(path).query_batch(seqs[: k * 150], off[: k + 1])
     assert np.array_equal(pml[: k * 150].astype(np.uint32), want_p) and np.array_equal(cid[: k * 150], want_c)
+
+
+def test_two_gpus_in_process_replicas(cb, small_index, monkeypatch):
+    """colbwt_index_load on 2 devices: chunks are dealt round-robin to the replicas, results land in input order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "30000")
+    seqs, off = small_index["seqs"], small_index["off"]
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"], devices=2)
+    assert tbl.stats.n_devices == 2
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    b = tbl.batch(seqs, off, device_slot=1)
+    b.run(1)
+    p2, c2 = b.download()
+    assert np.array_equal(p2.astype(np.uint32), want_p) and np.array_equal(c2, want_c)
+
+
+def test_narrow_layout_opt_in(cb, small_index, monkeypatch):
+    """COLBWT_NARROW=1 builds the 8-byte hot/cold layout; results must not change."""
+    monkeypatch.setenv("COLBWT_NARROW", "1")
+    tbl = cb.ColPml.load(small_index["path"])
+    extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
+    orc = oracle.Oracle(small_index["path"])
+    for seqs, off in ((small_index["seqs"], small_index["off"]), (extra, eoff)):
+        want_p, want_c = orc.query_batch(seqs, off)
+        pml, cid = tbl.query(seqs, off)
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
