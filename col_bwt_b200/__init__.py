@@ -46,6 +46,8 @@ class Stats(C.Structure):
 EXPORTS = {
     "colbwt_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "colbwt_index_from_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "colbwt_index_from_primaries": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "colbwt_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "colbwt_index_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "colbwt_index_free": (None, [C.c_void_p]),
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
@@ -186,6 +188,19 @@ class ColPml:
         h = C.c_void_p()
         _check(_L.colbwt_index_from_rows(raw.ctypes.data, bwt_r, n, raw.size // 18, arr, k, C.byref(h)), "colbwt_index_from_rows")
         return cls(h)
+
+    @classmethod
+    def from_primaries(cls, prefix: str, devices=None) -> "ColPml":
+        """col_pml(heads, lengths, col_ids, thresholds, splits) (col_bwt.hpp:391-395) built on the GPU from
+        PREFIX.{bwt.heads,bwt.len,thr_pos,col_runs,col_ids} -- what src/build_col_bwt.cpp does on the CPU."""
+        arr, k = _dev_array(devices)
+        h = C.c_void_p()
+        _check(_L.colbwt_index_from_primaries(os.fsencode(prefix), arr, k, C.byref(h)), "colbwt_index_from_primaries")
+        return cls(h)
+
+    def save(self, path: str) -> None:
+        """col_bwt::serialize (col_bwt.hpp:360-370): writes the `.col_pml` file."""
+        _check(_L.colbwt_index_save(self._h, os.fsencode(path)), "colbwt_index_save")
 
     def size(self) -> int:          # LF_table::size
         return self.n

@@ -3,6 +3,7 @@
 // one replaces.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 
@@ -69,6 +70,92 @@ static int build_index(const void *rows, FILE *fp, long data_start, uint64_t bwt
     return COLBWT_OK;
 }
 
+static bool read_file(const std::string &path, std::vector<uint8_t> &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(sz > 0 ? (size_t)sz : 0);
+    const bool ok = out.empty() || fread(out.data(), 1, out.size(), f) == out.size();
+    fclose(f);
+    return ok;
+}
+
+static void unpack_u40(const std::vector<uint8_t> &raw, std::vector<uint64_t> &out)
+{
+    out.resize(raw.size() / 5);
+    for (size_t i = 0; i < out.size(); ++i) {
+        uint64_t v = 0;
+        memcpy(&v, raw.data() + 5 * i, 5);   // little endian, RW_BYTES = 5 (common.hpp:46)
+        out[i] = v;
+    }
+}
+
+// prefix = the reference's `<out>.fa` stem (build_col_bwt.cpp:17-33 forms the same five names)
+static int load_primaries(const std::string &prefix, Primaries &pr)
+{
+    std::vector<uint8_t> raw;
+    if (!read_file(prefix + ".bwt.heads", pr.heads) || pr.heads.empty()) {
+        set_error("cannot read %s.bwt.heads", prefix.c_str());
+        return COLBWT_ERR_IO;
+    }
+    if (!read_file(prefix + ".bwt.len", raw)) {
+        set_error("cannot read %s.bwt.len", prefix.c_str());
+        return COLBWT_ERR_IO;
+    }
+    unpack_u40(raw, pr.lens);
+    if (!read_file(prefix + ".thr_pos", raw)) {
+        set_error("cannot read %s.thr_pos", prefix.c_str());
+        return COLBWT_ERR_IO;
+    }
+    unpack_u40(raw, pr.thr);
+    if (pr.lens.size() != pr.heads.size() || pr.thr.size() != pr.heads.size()) {
+        set_error("%s: %zu run heads but %zu lengths and %zu thresholds", prefix.c_str(), pr.heads.size(), pr.lens.size(), pr.thr.size());
+        return COLBWT_ERR_FORMAT;
+    }
+    if (!read_file(prefix + ".col_runs", raw) || raw.size() < 8) {
+        set_error("cannot read %s.col_runs", prefix.c_str());
+        return COLBWT_ERR_IO;
+    }
+    memcpy(&pr.n_bits, raw.data(), 8);   // sdsl bit_vector: u64 length in bits, then 64-bit words (col_split.hpp:384-386)
+    const uint64_t nw = (pr.n_bits + 63) / 64;
+    if (raw.size() < 8 + nw * 8) {
+        set_error("%s.col_runs: %zu bytes cannot hold a bit_vector of %llu bits (the sd_vector form is not supported)", prefix.c_str(),
+                  raw.size(), (unsigned long long)pr.n_bits);
+        return COLBWT_ERR_FORMAT;
+    }
+    pr.bits.resize(nw);
+    memcpy(pr.bits.data(), raw.data() + 8, nw * 8);
+    if (pr.n_bits & 63) pr.bits[nw - 1] &= (1ull << (pr.n_bits & 63)) - 1;
+    if (!read_file(prefix + ".col_ids", pr.ids)) {
+        set_error("cannot read %s.col_ids", prefix.c_str());
+        return COLBWT_ERR_IO;
+    }
+    uint64_t total = 0;
+    for (uint64_t l : pr.lens) {
+        if (l == 0) {
+            set_error("%s.bwt.len: a run of length 0", prefix.c_str());
+            return COLBWT_ERR_FORMAT;
+        }
+        total += l;
+    }
+    if (total != pr.n_bits) {
+        set_error("%s: run lengths sum to %llu but .col_runs has %llu bits", prefix.c_str(), (unsigned long long)total, (unsigned long long)pr.n_bits);
+        return COLBWT_ERR_FORMAT;
+    }
+    for (size_t i = 1; i < pr.heads.size(); ++i) {
+        const uint8_t a = pr.heads[i - 1], b = pr.heads[i];
+        const uint8_t ma = (a <= 1 || a >= 128) ? 1 : a, mb = (b <= 1 || b >= 128) ? 1 : b;
+        if (ma == mb) {   // read_thresholds (col_bwt.hpp:450-453) would give both runs one threshold and drift out of step
+            set_error("%s.bwt.heads: runs %zu and %zu carry the same character after terminator folding", prefix.c_str(), i - 1, i);
+            return COLBWT_ERR_FORMAT;
+        }
+    }
+    return COLBWT_OK;
+}
+
 } // namespace colbwt
 
 using namespace colbwt;
@@ -120,6 +207,64 @@ extern "C" int colbwt_index_from_rows(const void *rows, uint64_t bwt_r, uint64_t
     std::vector<int> devs;
     if (int rc = device_list(devices, n_devices, devs)) return rc;
     return build_index(rows, nullptr, 0, bwt_r, n, r, devs, out);
+}
+
+extern "C" int colbwt_index_from_primaries(const char *prefix, const int *devices, int n_devices, colbwt_index **out)
+{
+    if (!prefix || !out) {
+        set_error("colbwt_index_from_primaries: null argument");
+        return COLBWT_ERR_ARG;
+    }
+    Primaries pr;
+    if (int rc = load_primaries(prefix, pr)) return rc;
+    std::vector<int> devs;
+    if (int rc = device_list(devices, n_devices, devs)) return rc;
+    std::unique_ptr<colbwt_index> idx(new colbwt_index);
+    idx->dev.resize(devs.size());
+    idx->stats.bwt_r = pr.heads.size();
+    idx->stats.n_devices = (int)devs.size();
+    for (size_t i = 0; i < devs.size(); ++i) {
+        uint64_t n = 0, r = 0;
+        int rc = build_device_table_from_primaries(idx->dev[i], devs[i], pr, i == 0 ? &idx->stats : nullptr, idx->code_lut, &n, &r);
+        if (rc != COLBWT_OK) {
+            for (auto &d : idx->dev) free_device_table(d);
+            return rc;
+        }
+        idx->stats.n = n;
+        idx->stats.r = r;
+    }
+    *out = idx.release();
+    return COLBWT_OK;
+}
+
+extern "C" int colbwt_index_save(const colbwt_index *idx, const char *path)
+{
+    if (!idx || !path || idx->dev.empty()) {
+        set_error("colbwt_index_save: null argument");
+        return COLBWT_ERR_ARG;
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        set_error("cannot write %s", path);
+        return COLBWT_ERR_IO;
+    }
+    std::unique_ptr<FILE, int (*)(FILE *)> guard(f, fclose);
+    const uint64_t hdr[4] = {idx->stats.bwt_r, idx->stats.n, idx->stats.r, idx->stats.r};   // col_bwt.hpp:364, LF_table.hpp:329-337
+    if (fwrite(hdr, 8, 4, f) != 4) {
+        set_error("short write to %s", path);
+        return COLBWT_ERR_IO;
+    }
+    const uint64_t chunk = 4u << 20;
+    std::vector<uint8_t> buf(chunk * 18);
+    for (uint64_t first = 0; first < idx->stats.r; first += chunk) {
+        const uint64_t count = std::min<uint64_t>(chunk, idx->stats.r - first);
+        if (int rc = export_rows(idx->dev[0], first, count, buf.data())) return rc;
+        if (fwrite(buf.data(), 18, count, f) != count) {
+            set_error("short write to %s", path);
+            return COLBWT_ERR_IO;
+        }
+    }
+    return COLBWT_OK;
 }
 
 extern "C" int colbwt_index_stats(const colbwt_index *idx, colbwt_stats *out)

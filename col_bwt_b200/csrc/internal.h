@@ -55,6 +55,20 @@ int build_device_table(DeviceTable &dt, int device, const void *rows, FILE *fp, 
                        colbwt_stats *stats, uint8_t *code_lut_out);
 void free_device_table(DeviceTable &dt);
 
+// The files `col-bwt build --keep` leaves on disk, read into host memory (capi.cpp: load_primaries).
+struct Primaries {
+    std::vector<uint8_t> heads;     // .bwt.heads   1 byte per BWT run
+    std::vector<uint64_t> lens;     // .bwt.len     5-byte LE per run
+    std::vector<uint64_t> thr;      // .thr_pos     5-byte LE per run
+    std::vector<uint64_t> bits;     // .col_runs    sdsl bit_vector words (LSB first), n_bits of them used
+    std::vector<uint8_t> ids;       // .col_ids     1 byte per set bit
+    uint64_t n_bits = 0;
+};
+int build_device_table_from_primaries(DeviceTable &dt, int device, const Primaries &pr, colbwt_stats *stats, uint8_t *code_lut_out,
+                                      uint64_t *n_out, uint64_t *r_out);
+// 18-byte reference rows [first, first+count) reconstructed from the device columns.
+int export_rows(const DeviceTable &dt, uint64_t first, uint64_t count, void *host_out);
+
 // pack.cpp: host-side 2-bit packer.
 // Packs reads [r0, r1) of a batch: 2-bit words at word offsets word_off[i] (relative to words),
 // returns false for reads that contain a byte outside ACGT (their words are garbage, caller ships bytes).

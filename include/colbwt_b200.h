@@ -9,6 +9,8 @@
  *                            (called from src/pml_query.cpp:110-113)
  *   colbwt_index_from_rows   the same, from memory (rows as read_vec would fill them,
  *                            include/common/common.hpp:318-323)
+ *   colbwt_index_from_primaries / colbwt_index_save
+ *                            src/build_col_bwt.cpp:8-64 (constructors + serialize), on the GPU
  *   colbwt_index_stats       col_bwt::bwt_stats / runs / size        include/col_bwt.hpp:331-344
  *   colbwt_query             col_pml::query_pml(const char*, size_t) include/col_bwt.hpp:409-412, for a whole
  *                            batch of reads (the per-read loop of src/pml_query.cpp:74-86)
@@ -74,6 +76,17 @@ int colbwt_index_load(const char *path, const int *devices, int n_devices, colbw
 /* Same from memory: `rows` = r packed 18-byte col_thr rows exactly as they sit in the file. */
 int colbwt_index_from_rows(const void *rows, uint64_t bwt_r, uint64_t n, uint64_t r,
                            const int *devices, int n_devices, colbwt_index **out);
+
+/* Build the table on the GPU from the primaries that `col-bwt build --keep` leaves on disk, without the `.col_pml`
+ * intermediate: PREFIX.bwt.heads, PREFIX.bwt.len, PREFIX.thr_pos, PREFIX.col_runs (sdsl bit_vector as written by
+ * col_split.hpp:384-386) and PREFIX.col_ids.  Replaces src/build_col_bwt.cpp:8-64, i.e. the constructor
+ * col_bwt(heads, lengths, col_ids, splits) (include/col_bwt.hpp:124-230), LF_table::compute_table
+ * (include/ds/LF_table.hpp:365-387) and col_pml::read_thresholds (include/col_bwt.hpp:440-457). */
+int colbwt_index_from_primaries(const char *prefix, const int *devices, int n_devices, colbwt_index **out);
+
+/* Write the table as `.col_pml` (col_bwt::serialize, include/col_bwt.hpp:360-370 + LF_table.hpp:325-342): byte-identical
+ * to what the reference's build_col_bwt writes for the same primaries. */
+int colbwt_index_save(const colbwt_index *idx, const char *path);
 
 int colbwt_index_stats(const colbwt_index *idx, colbwt_stats *out);
 void colbwt_index_free(colbwt_index *idx);

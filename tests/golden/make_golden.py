@@ -4,6 +4,7 @@ oracle/Makefile) -- needs /root/reference, so it runs in the build container onl
 
 Cases
   toy   : the known-answer vector of SURVEY.md section 4.3 (hand-chosen splits, thresholds from the text).
+  pan4all: the same text with `col_split -m all -s 2` (marks every multi-MUM column range, overlaps resolved).
   pan4  : 4 haplotypes x 6 kbp (+reverse complements), 0.5 % SNPs, indels; primaries from synthdata; marks from the
           reference's build_FL + col_split -m tunnels -s 4; table from the reference's build_col_bwt; expected
           PML/CID text from the reference's pml_query exactly as shipped (MULTI_THREAD on).
@@ -56,13 +57,16 @@ def toy(tmp):
         shutil.copy(src, os.path.join(OUT, dst))
 
 
-def pan4(tmp):
+def pan4(tmp, name="pan4", mode="tunnels", rate="4"):
     haps = P.make_haplotypes(6000, 4, snp=5e-3, indel=5e-4, seed=42)
     idx = PL.build_index(haps, split_rate=4)
-    p = os.path.join(tmp, "pan4.fa")
+    p = os.path.join(tmp, name + ".fa")
     PL.write_reference_inputs(p, idx)
     run(os.path.join(REF, "build_FL"), p)
-    run(os.path.join(REF, "col_split"), p, "-m", "tunnels", "-s", "4")
+    run(os.path.join(REF, "col_split"), p, "-m", mode, "-s", rate)
+    # the primaries as the reference tools leave them: inputs of colbwt_index_from_primaries
+    for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_runs", ".col_ids"):
+        shutil.copy(p + ext, os.path.join(OUT, name + ".fa" + ext))
     n, pos = F.read_bit_vector(p + ".col_runs")           # col_split writes a plain bit_vector ...
     F.write_shim_sd_vector(p + ".col_runs", n, pos)        # ... build_col_bwt loads an sd_vector
     run(os.path.join(REF, "build_col_bwt"), p)
@@ -70,14 +74,14 @@ def pan4(tmp):
     reads = [bytes(seqs[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
     reads += [b"N" * 30, b"acgtacgtnnACGT", b"A", b"ACGTNACGTTTGACNNNNACGATCGATCGATCGACTGACTAGCTAGCTAGC",
               bytes(haps[1][500:900]), bytes(haps[2][10:70]).lower(), b"G" * 120, b"\x01ACGT\x01", b"TTTTTTTTTTNTTTTTTTTT"]
-    rp = os.path.join(tmp, "pan4_reads.fa")
+    rp = os.path.join(tmp, name + "_reads.fa")
     names = [f"r{i}" for i in range(len(reads))]
     F.write_fasta(rp, reads, names=names)
     with open(rp, "ab") as f:   # a zero-length record and a multi-line record with a comment
         f.write(b">empty\n\n>multi some comment\nACGTAC\nGTTGCA\nAC\n")
     run(os.path.join(REF, "pml_query"), p, "-p", rp)
-    for src, dst in ((p + ".col_pml", "pan4.col_pml"), (rp, "pan4_reads.fa"), (rp + ".pml", "pan4_reads.fa.pml"),
-                     (rp + ".cid", "pan4_reads.fa.cid")):
+    for src, dst in ((p + ".col_pml", name + ".col_pml"), (rp, name + "_reads.fa"), (rp + ".pml", name + "_reads.fa.pml"),
+                     (rp + ".cid", name + "_reads.fa.cid")):
         shutil.copy(src, os.path.join(OUT, dst))
 
 
@@ -85,4 +89,5 @@ if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as tmp:
         toy(tmp)
         pan4(tmp)
+        pan4(tmp, name="pan4all", mode="all", rate="2")   # BASELINE configs[3]: non-tunnel marking, denser sub-sampling
     print("golden fixtures written to", OUT)

@@ -18,7 +18,7 @@ def cols_from_file(path):
             "col_id": rows["col_id"], "thr": F.u40_unpack(rows["thr"]), "n": meta["n"], "bwt_r": meta["bwt_r"]}
 
 
-@pytest.mark.parametrize("case", ["toy", "pan4"])
+@pytest.mark.parametrize("case", ["toy", "pan4", "pan4all"])
 @pytest.mark.parametrize("width", [2, 4])
 @pytest.mark.parametrize("force_bytes", [False, True])
 @pytest.mark.parametrize("narrow", [False, True])

@@ -21,7 +21,7 @@ def cb():
     return col_bwt_b200
 
 
-@pytest.mark.parametrize("case", ["toy", "pan4"])
+@pytest.mark.parametrize("case", ["toy", "pan4", "pan4all"])
 def test_golden_text_matches_reference_pml_query(cb, golden_dir, case):
     """Golden .pml/.cid are the bytes the reference's pml_query wrote; format through the C-ABI and compare bytes."""
     tbl = cb.ColPml.load(os.path.join(golden_dir, f"{case}.col_pml"))
@@ -260,3 +260,53 @@ def test_narrow_layout_opt_in(cb, small_index, monkeypatch):
         want_p, want_c = orc.query_batch(seqs, off)
         pml, cid = tbl.query(seqs, off)
         assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("case", ["pan4", "pan4all"])
+def test_index_from_primaries_is_byte_identical_to_reference_build_col_bwt(cb, golden_dir, tmp_path, case):
+    """GPU table construction from .bwt.heads/.bwt.len/.thr_pos/.col_runs/.col_ids (as the reference's tools left
+    them) == the `.col_pml` the reference's build_col_bwt wrote, byte for byte; and it answers queries identically."""
+    tbl = cb.ColPml.from_primaries(os.path.join(golden_dir, case + ".fa"))
+    out = tmp_path / "rebuilt.col_pml"
+    tbl.save(str(out))
+    assert out.read_bytes() == open(os.path.join(golden_dir, case + ".col_pml"), "rb").read()
+    ids, seqs, off = parse_fastx(os.path.join(golden_dir, f"{case}_reads.fa"))
+    pml, cid = tbl.query(seqs, off, cb.PML_U32)
+    txt_p = b"".join(cb.format_stats(ids[i], pml[int(off[i]):int(off[i + 1])]) for i in range(len(ids)))
+    txt_c = b"".join(cb.format_stats(ids[i], cid[int(off[i]):int(off[i + 1])]) for i in range(len(ids)))
+    assert txt_p == open(os.path.join(golden_dir, f"{case}_reads.fa.pml"), "rb").read()
+    assert txt_c == open(os.path.join(golden_dir, f"{case}_reads.fa.cid"), "rb").read()
+
+
+def test_index_from_primaries_matches_tooling_at_scale(cb, small_index, tmp_path):
+    """Same on the 240 kbp synthetic index: rows == synthdata.table.build_columns (itself pinned to build_col_bwt)."""
+    idx = small_index["idx"]
+    p = str(tmp_path / "s.fa")
+    F.write_primaries(p, idx["heads"], idx["lens"], idx["thr_run"])
+    F.write_bit_vector(p + ".col_runs", small_index["cols"]["n"], idx["split_pos"])
+    np.asarray(idx["split_ids"], np.uint8).tofile(p + ".col_ids")
+    tbl = cb.ColPml.from_primaries(p)
+    tbl.save(p + ".col_pml")
+    assert open(p + ".col_pml", "rb").read() == open(small_index["path"], "rb").read()
+    # load -> save round trip
+    cb.ColPml.load(small_index["path"]).save(p + ".2")
+    assert open(p + ".2", "rb").read() == open(small_index["path"], "rb").read()
+
+
+def test_index_from_primaries_errors_and_cli(cb, golden_dir, tmp_path):
+    import shutil
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.from_primaries(str(tmp_path / "nope.fa"))
+    assert e.value.code == -1
+    for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_runs", ".col_ids"):
+        shutil.copy(os.path.join(golden_dir, "pan4.fa" + ext), tmp_path / ("x.fa" + ext))
+    ids = (tmp_path / "x.fa.col_ids").read_bytes()
+    (tmp_path / "x.fa.col_ids").write_bytes(ids[:-3])                 # fewer ids than set bits
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.ColPml.from_primaries(str(tmp_path / "x.fa"))
+    assert e.value.code == -2
+    (tmp_path / "x.fa.col_ids").write_bytes(ids)
+    cli = os.path.join(ROOT, "col_bwt_b200", "bin", "build_col_bwt_b200")
+    r = subprocess.run([cli, str(tmp_path / "x.fa")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "x.fa.col_pml").read_bytes() == open(os.path.join(golden_dir, "pan4.col_pml"), "rb").read()

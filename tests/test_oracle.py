@@ -8,7 +8,7 @@ import oracle
 from util import adversarial_reads, check_pml_properties, concat_reads, parse_fastx
 
 
-@pytest.mark.parametrize("case", ["toy", "pan4"])
+@pytest.mark.parametrize("case", ["toy", "pan4", "pan4all"])
 def test_oracle_matches_reference_golden_text(golden_dir, case):
     """Golden .pml/.cid were written by the reference's pml_query as shipped (tests/golden/make_golden.py)."""
     orc = oracle.Oracle(os.path.join(golden_dir, f"{case}.col_pml"))
