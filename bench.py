@@ -43,9 +43,11 @@ WORKLOADS = {
     "c2small": dict(H=32, G=1_000_000, snp=9e-4, indel=1e-4, reads=2_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
     "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=400_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
 }
+WORKLOADS["c5small"] = dict(synthetic_rows=250_000_000, mean_len=16.0, reads=10_000_000, read_len=150, sub=0.01)
 WORKLOADS["tiny"] = dict(H=4, G=50_000, snp=1e-3, indel=0.0, reads=5_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False)
 WORKLOAD_TEXT = {
     "tiny": "4-haplotype x 50 kbp toy (CPU self-test of bench.py only)",
+    "c5small": "configs[4] scaled to 2.5e8 directly synthesised move rows (4 GB packed table, DRAM-resident), 10M x 150 bp LF-walk reads, 1% substitutions",
     "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
     "c2small": "configs[1] scaled down 10x in genome length and 5x in reads (smoke runs only)",
@@ -117,6 +119,8 @@ def build_workload(name: str, device: str, verbose: bool):
     w = WORKLOADS[name]
     stem = os.path.join(cache_dir(), name)
     meta_path = stem + ".meta.json"
+    if "synthetic_rows" in w:
+        return build_synthetic_table(name, device, verbose)
     if not os.path.exists(meta_path):
         t0 = time.time()
         haps = P.make_haplotypes(w["G"], w["H"], snp=w["snp"], indel=w["indel"], seed=1, tree=w["tree"])
@@ -134,10 +138,49 @@ def build_workload(name: str, device: str, verbose: bool):
     return stem + ".col_pml", np.load(stem + ".text.npy", mmap_mode="r"), np.load(stem + ".seq_starts.npy"), meta
 
 
+def build_synthetic_table(name: str, device: str, verbose: bool):
+    """configs[4]-style workload: a directly synthesised move table (no text).  The table file and one set of LF-walk
+    reads per rank seed are cached; `text` is returned as None and `seq_starts` carries the cache stem instead."""
+    import torch
+    from synthdata import pipeline as PL
+    w = WORKLOADS[name]
+    stem = os.path.join(cache_dir(), name)
+    meta_path = stem + ".meta.json"
+    if not os.path.exists(meta_path):
+        t0 = time.time()
+        rows, n, cols = PL.synth_move_table(w["synthetic_rows"], mean_len=w["mean_len"], device=device)
+        with open(stem + ".col_pml", "wb") as f:
+            f.write(np.array([rows.shape[0], n, rows.shape[0], rows.shape[0]], dtype="<u8").tobytes())
+            step = 1 << 24
+            for a in range(0, rows.shape[0], step):
+                f.write(rows[a:a + step].cpu().numpy().tobytes())
+        del rows
+        torch.cuda.empty_cache()
+        for seed_rank in range(int(os.environ.get("WORLD_SIZE", "1"))):
+            seqs, off = PL.walk_reads(cols, w["reads"], w["read_len"], sub=w["sub"], seed=6 + seed_rank)
+            np.save(stem + f".reads{seed_rank}.npy", seqs)
+        meta = {"n": int(n), "r": int(w["synthetic_rows"]), "bwt_r": int(w["synthetic_rows"]), "mums": 0, "marked_rows": -1,
+                "build_s": time.time() - t0}
+        del cols
+        torch.cuda.empty_cache()
+        with open(meta_path + ".tmp", "w") as f:
+            json.dump(meta, f)
+        os.replace(meta_path + ".tmp", meta_path)
+        if verbose:
+            print(f"[bench] synthetic table {name}: {meta}", file=sys.stderr, flush=True)
+    return stem + ".col_pml", None, stem, json.load(open(meta_path))
+
+
 def make_reads(name: str, text, seq_starts, rank: int, n_reads: int | None, device: str):
     from synthdata import pangenome as P
     w = WORKLOADS[name]
     n = n_reads or w["reads"]
+    if text is None:   # synthetic table: cached LF-walk reads (seq_starts is the cache stem)
+        path = f"{seq_starts}.reads{rank}.npy"
+        if not os.path.exists(path):
+            path = f"{seq_starts}.reads0.npy"
+        seqs = np.load(path)[: n * w["read_len"]]
+        return np.ascontiguousarray(seqs), np.arange(n + 1, dtype=np.uint64) * np.uint64(w["read_len"])
     return P.sample_reads_device(np.asarray(text), seq_starts, n, w["read_len"], sub=w["sub"], ins=w["ins"], dele=w["dele"],
                                  len_sigma=w["len_sigma"], seed=2 + rank, device=device)
 

@@ -101,70 +101,23 @@ constexpr uint32_t BUILD_FLAG_BAD_LEN = 1u;   // row of length 0 or >= 65536
 constexpr uint32_t BUILD_FLAG_SLOW = 2u;      // some (row, character) needs the exact search
 constexpr uint32_t BUILD_FLAG_BAD_LF = 4u;    // dest >= r
 
-// L2 residency policy handles (createpolicy): the table is kept (evict_last), everything streamed once -- packed
-// reads in, PML/CID out -- is marked evict_first so that it does not push table lines out of the 126 MB L2.
-struct Policies {
-    uint64_t keep = 0, stream = 0;
-};
-
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-__device__ __forceinline__ Policies make_policies()
+CB_HD Row ld_row(const Row *p)
 {
-    Policies p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
-    return p;
-}
-template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &pol)
-{
-    uint4 v;
-    if (HINTS)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol.keep));
-    else
-        v = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));   // LDG.E.128.CONSTANT: one 128-bit read-only gather
     return Row{v.x, v.y, v.z, v.w};
 }
+CB_HD uint64_t ld_row64(const uint64_t *p) { return __ldg(reinterpret_cast<const unsigned long long *>(p)); }
 template <typename T> CB_HD T ld_ro(const T *p) { return __ldg(p); }
-template <int HINTS> CB_HD uint64_t ld_row64(const uint64_t *p, const Policies &pol)
-{
-    if (!HINTS) return __ldg(reinterpret_cast<const unsigned long long *>(p));
-    uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol.keep));
-    return v;
-}
-template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &pol)
-{
-    if (!HINTS) return __ldg(p);
-    uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol.stream));
-    return v;
-}
-template <int HINTS> CB_HD void st_stream_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Policies &pol)
-{
-    if (HINTS == 2) return;   // experiment: no output traffic
-    if (HINTS)
-        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol.stream) : "memory");
-    else
-        *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
-}
-template <int HINTS> CB_HD void st_stream_v2(void *p, uint32_t a, uint32_t b, const Policies &pol)
-{
-    if (HINTS == 2) return;
-    if (HINTS)
-        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol.stream) : "memory");
-    else
-        *reinterpret_cast<uint2 *>(p) = make_uint2(a, b);
-}
+CB_HD void st_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d); }
+CB_HD void st_v2(void *p, uint32_t a, uint32_t b) { *reinterpret_cast<uint2 *>(p) = make_uint2(a, b); }
 #else
-CB_HD Policies make_policies() { return Policies{}; }
-template <int HINTS> CB_HD void st_stream_v4(void *, uint32_t, uint32_t, uint32_t, uint32_t, const Policies &) {}
-template <int HINTS> CB_HD void st_stream_v2(void *, uint32_t, uint32_t, const Policies &) {}
-template <int HINTS> CB_HD Row ld_row(const Row *p, const Policies &) { return *p; }
-template <int HINTS> CB_HD uint64_t ld_row64(const uint64_t *p, const Policies &) { return *p; }
+CB_HD Row ld_row(const Row *p) { return *p; }
+CB_HD uint64_t ld_row64(const uint64_t *p) { return *p; }
 template <typename T> CB_HD T ld_ro(const T *p) { return *p; }
-template <int HINTS> CB_HD uint32_t ld_stream_u32(const uint32_t *p, const Policies &) { return *p; }
 #endif
+// (L2 eviction-priority hints -- evict_last on the table, evict_first on the streams -- were measured and dropped:
+//  no gain on this access pattern, profiles/r1/variant_sweep1.log.)
 
 // Build the packed row k from the reference columns.  Pure function of the columns.
 CB_HD Row build_row(const BuildView &b, uint32_t k, uint32_t *flags)
@@ -291,16 +244,16 @@ template <typename PmlT> struct Lane {
     uint32_t accc[2] = {0, 0};         // 8 staged CID bytes
 };
 
-template <int HINTS, typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g, const Policies &pol)
+template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g)
 {
     uint8_t *cid = bv.cid + g;
     if (L.cnt == 8) {   // aligned full group: g % 8 == 0
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-        st_stream_v2<HINTS>(cid, L.accc[0], L.accc[1], pol);
+        st_v2(cid, L.accc[0], L.accc[1]);
         if (sizeof(PmlT) == 2)
-            st_stream_v4<HINTS>(reinterpret_cast<uint16_t *>(bv.pml) + g, L.accp[0], L.accp[1], L.accp[2], L.accp[3], pol);
+            st_v4(reinterpret_cast<uint16_t *>(bv.pml) + g, L.accp[0], L.accp[1], L.accp[2], L.accp[3]);
         else if (sizeof(PmlT) == 1)
-            st_stream_v2<HINTS>(reinterpret_cast<uint8_t *>(bv.pml) + g, L.accp[0], L.accp[1], pol);
+            st_v2(reinterpret_cast<uint8_t *>(bv.pml) + g, L.accp[0], L.accp[1]);
 #else
         for (int t = 0; t < 8; ++t) cid[t] = (uint8_t)(L.accc[t >> 2] >> (8 * (t & 3)));
         if (sizeof(PmlT) == 2)
@@ -331,7 +284,7 @@ template <int HINTS, typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const B
     L.cnt = 0;
 }
 
-template <int HINTS, typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid, const Policies &pol)
+template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)
 {
     const uint64_t g = L.out_base + jj;
     L.accc[1] = (L.accc[1] << 8) | (L.accc[0] >> 24);
@@ -348,12 +301,11 @@ template <int HINTS, typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const Ba
         reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
     }
     ++L.cnt;
-    if ((g & 7) == 0 || jj == 0) lane_flush<HINTS>(L, bv, g, pol);
+    if ((g & 7) == 0 || jj == 0) lane_flush(L, bv, g);
 }
 
 // Start read `m` on this lane (zero-length reads are skipped by the caller).
-template <bool PACKED, int HINTS, typename PmlT>
-CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ReadMeta &m, const Policies &pol)
+template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ReadMeta &m)
 {
     L.state = LANE_LF;
     L.addr = t.r - 1;               // col_bwt.hpp:504
@@ -363,12 +315,12 @@ CB_HD void lane_begin(Lane<PmlT> &L, const TableView &t, const BatchView &bv, co
     L.in_off = m.in_off;
     L.out_base = m.out_off;
     L.cnt = 0;
-    if (PACKED) L.rw = ld_stream_u32<HINTS>(bv.words + m.in_off + ((m.len - 1) >> 4), pol);
+    if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
 }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
-template <bool PACKED, int HINTS, typename PmlT>
-CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut, const Policies &pol)
+template <bool PACKED, typename PmlT>
+CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
 {
     const uint32_t len = row_len(row);
     if (L.state != LANE_LF) {
@@ -390,7 +342,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     uint8_t cbyte = 0;
     if (PACKED) {
         code = (L.rw >> (2 * (jj & 15))) & 3u;
-        if ((jj & 15) == 0 && jj != 0) L.rw = ld_stream_u32<HINTS>(bv.words + L.in_off + ((jj - 1) >> 4), pol);
+        if ((jj & 15) == 0 && jj != 0) L.rw = ld_ro(bv.words + L.in_off + ((jj - 1) >> 4));
     } else {
         cbyte = ld_ro(bv.bytes + L.in_off + jj);
         code = code_lut[cbyte];
@@ -405,7 +357,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     } else {
         L.plen = 0;                              // col_bwt.hpp:520-523
     }
-    lane_emit<HINTS>(L, bv, jj, L.plen, cid, pol);
+    lane_emit(L, bv, jj, L.plen, cid);
     if (jj == 0) {                               // the reference's last LF step has no observable effect
         L.state = LANE_IDLE;
         return;
@@ -442,9 +394,8 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
 
 
 // Narrow-layout twin of lane_step.  `w` = hot[addr], or cold[addr] when the lane is in LANE_COLD.
-template <bool PACKED, int HINTS, typename PmlT>
-CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut,
-                            const Policies &pol)
+template <bool PACKED, typename PmlT>
+CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut)
 {
     const uint32_t st = L.state & 7u;
     if (st == LANE_COLD) {
@@ -494,7 +445,7 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
     uint8_t cbyte = 0;
     if (PACKED) {
         code = (L.rw >> (2 * (jj & 15))) & 3u;
-        if ((jj & 15) == 0 && jj != 0) L.rw = ld_stream_u32<HINTS>(bv.words + L.in_off + ((jj - 1) >> 4), pol);
+        if ((jj & 15) == 0 && jj != 0) L.rw = ld_ro(bv.words + L.in_off + ((jj - 1) >> 4));
     } else {
         cbyte = ld_ro(bv.bytes + L.in_off + jj);
         code = code_lut[cbyte];
@@ -503,7 +454,7 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
     if (!PACKED && code >= CODE_OTHER)
         match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
     L.plen = match ? L.plen + 1 : 0;
-    lane_emit<HINTS>(L, bv, jj, L.plen, cid, pol);
+    lane_emit(L, bv, jj, L.plen, cid);
     if (jj == 0) {
         L.state = LANE_IDLE;
         return;

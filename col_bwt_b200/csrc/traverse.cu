@@ -16,7 +16,7 @@ namespace colbwt {
 
 constexpr int TRAVERSE_THREADS = 256;
 
-template <bool PACKED, typename PmlT, int HINTS, int CTAS, bool NARROW>
+template <bool PACKED, typename PmlT, int CTAS, bool NARROW>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
@@ -28,7 +28,6 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     const uint32_t lane = threadIdx.x & 31;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const uint32_t count = PACKED ? bv.n_packed : bv.n_bytes;
-    const Policies pol = HINTS == 1 ? make_policies() : Policies{};
     Lane<PmlT> L;
     bool exhausted = false;
     for (;;) {
@@ -47,7 +46,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
                     m.out_off = (uint64_t)mv.x | ((uint64_t)mv.y << 32);
                     m.len = mv.z;
                     m.in_off = mv.w;
-                    if (m.len) lane_begin<PACKED, HINTS>(L, t, bv, m, pol);   // zero-length read: nothing to emit
+                    if (m.len) lane_begin<PACKED>(L, t, bv, m);   // zero-length read: nothing to emit
                 } else {
                     exhausted = true;
                 }
@@ -58,44 +57,33 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
         if (L.state != LANE_IDLE) {
             if (NARROW) {
                 const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
-                const uint64_t w = ld_row64<HINTS>(base + L.addr, pol);
-                lane_step_narrow<PACKED, HINTS>(L, t, bv, w, code_lut, pol);
+                const uint64_t w = ld_row64(base + L.addr);
+                lane_step_narrow<PACKED>(L, t, bv, w, code_lut);
             } else {
-                const Row row = ld_row<HINTS>(t.rows + L.addr, pol);
-                lane_step<PACKED, HINTS>(L, t, bv, row, code_lut, pol);
+                const Row row = ld_row(t.rows + L.addr);
+                lane_step<PACKED>(L, t, bv, row, code_lut);
             }
         }
     }
 }
 
+// CTAs per SM: 4 (1024 lanes per SM, 48 registers, no spills) is the measured optimum on DRAM-resident tables -- more
+// lanes in flight only thrash the L2 (profiles/r1/variant_sweep2.log); COLBWT_CTAS=8 selects the full-occupancy build.
 template <bool PACKED, typename PmlT>
-static void launch_variant(int variant, unsigned grid_per_cta8, int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv,
-                           const uint8_t *lut, unsigned long long *cursor, cudaStream_t stream)
+static void launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut,
+                       unsigned long long *cursor, cudaStream_t stream)
 {
-    (void)grid_per_cta8;
-    auto grid_for = [&](int ctas) {
-        const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
-        return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
-    };
-    static const int ctas = getenv("COLBWT_CTAS") ? atoi(getenv("COLBWT_CTAS")) : 4;
+    static const int ctas = (getenv("COLBWT_CTAS") && atoi(getenv("COLBWT_CTAS")) == 8) ? 8 : 4;
+    const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
     const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
-    (void)variant;
-    static const bool nostore = getenv("COLBWT_NOSTORE") != nullptr;   // experiment only: results are not written
-#define CB_LAUNCH(C)                                                                                                        \
-    do {                                                                                                                    \
-        if (nostore) k_traverse<PACKED, PmlT, 2, C, true><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);  \
-        else if (narrow) k_traverse<PACKED, PmlT, 0, C, true><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);  \
-        else k_traverse<PACKED, PmlT, 0, C, false><<<grid_for(C), TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);        \
-    } while (0)
-    switch (ctas) {
-    case 2: CB_LAUNCH(2); break;
-    case 3: CB_LAUNCH(3); break;
-    case 5: CB_LAUNCH(5); break;
-    case 6: CB_LAUNCH(6); break;
-    case 8: CB_LAUNCH(8); break;
-    default: CB_LAUNCH(4); break;
+    if (ctas == 8) {
+        if (narrow) k_traverse<PACKED, PmlT, 8, true><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
+        else k_traverse<PACKED, PmlT, 8, false><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
+    } else {
+        if (narrow) k_traverse<PACKED, PmlT, 4, true><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
+        else k_traverse<PACKED, PmlT, 4, false><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
     }
-#undef CB_LAUNCH
 }
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)
@@ -104,15 +92,15 @@ int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, u
     CB_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned long long), stream));
     const uint8_t *lut = (const uint8_t *)dt.d_code_lut;
     if (bv.n_packed) {
-        if (pml_width == 2) launch_variant<true, uint16_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
-        else if (pml_width == 1) launch_variant<true, uint8_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
-        else launch_variant<true, uint32_t>(0, 0, dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        if (pml_width == 2) launch_one<true, uint16_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else if (pml_width == 1) launch_one<true, uint8_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else launch_one<true, uint32_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         CB_CUDA(cudaGetLastError());
     }
     if (bv.n_bytes) {
-        if (pml_width == 2) launch_variant<false, uint16_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
-        else if (pml_width == 1) launch_variant<false, uint8_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
-        else launch_variant<false, uint32_t>(0, 0, dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        if (pml_width == 2) launch_one<false, uint16_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else if (pml_width == 1) launch_one<false, uint8_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else launch_one<false, uint32_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         CB_CUDA(cudaGetLastError());
     }
     return COLBWT_OK;

@@ -62,3 +62,104 @@ def write_reference_inputs(prefix: str, idx: dict) -> None:
     """The files the reference's own build tools read: prefix.{bwt.heads,bwt.len,thr_pos,col_mums}."""
     formats.write_primaries(prefix, idx["heads"], idx["lens"], idx["thr_run"])
     formats.write_col_mums(prefix + ".col_mums", idx["num_docs"], idx["mum_len"], idx["mum_pos"])
+
+
+def synth_move_table(r: int, *, mean_len: float = 16.0, mark_frac: float = 0.08, seed: int = 5, device="cuda"):
+    """Directly synthesised valid move table with r rows (BASELINE configs[4]: index scaled to an HPRC-like run count
+    without building a text): random run characters (adjacent runs differ) and lengths, LF columns from the stable
+    character sort exactly as LF_table::compute_table derives them, thresholds uniform in the legal gap
+    (end of previous run of the character, start of this run], random chain ids on a fraction of the rows, and one
+    terminator row.  Returns (rows_u8 [r,18] torch tensor on `device` in the `.col_pml` row layout, n, dict of
+    LF columns for walking).  Everything stays on `device`."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dev = torch.device(device)
+    # characters: codes 0..3 with c[i] != c[i-1]; row r//2 becomes the terminator (byte 1)
+    inc = torch.randint(1, 4, (r,), generator=g, device=dev, dtype=torch.int64)
+    code = torch.cumsum(inc, 0) % 4
+    acgt = torch.tensor([ord(x) for x in "ACGT"], dtype=torch.uint8, device=dev)
+    ch = acgt[code]
+    term = r // 2
+    ch[term] = 1
+    # lengths: 1 + geometric, capped (the reference's 16-bit offsets need rows < 65536)
+    u = torch.rand(r, generator=g, device=dev, dtype=torch.float64)
+    lens = (1 + torch.floor(torch.log(1 - u) / np.log(1 - 1.0 / mean_len))).clamp(1, 1000).to(torch.int64)
+    lens[term] = 1
+    idx = torch.cumsum(lens, 0) - lens
+    n = int(lens.sum())
+    # compute_table: stable order by character byte
+    _, order = torch.sort(ch, stable=True)
+    ls = lens[order]
+    fpos = torch.cumsum(ls, 0) - ls
+    dest_s = torch.searchsorted(idx, fpos, right=True) - 1
+    doff_s = fpos - idx[dest_s]
+    dest = torch.empty(r, dtype=torch.int64, device=dev)
+    doff = torch.empty(r, dtype=torch.int64, device=dev)
+    dest[order] = dest_s
+    doff[order] = doff_s
+    del dest_s, doff_s, fpos, ls
+    # thresholds: previous row of the same character is the previous entry of the same character group in `order`
+    chs = ch[order]
+    prev = torch.roll(order, 1)
+    same = torch.ones(r, dtype=torch.bool, device=dev)
+    same[0] = False
+    same[1:] = chs[1:] == chs[:-1]
+    lo = idx[prev] + lens[prev]                       # first position after the previous run of the character
+    hi = idx[order]                                   # start of this run
+    uu = torch.rand(r, generator=g, device=dev, dtype=torch.float64)
+    t = lo + torch.floor(uu * (hi - lo + 1).to(torch.float64)).to(torch.int64)
+    thr = torch.zeros(r, dtype=torch.int64, device=dev)
+    thr[order] = torch.where(same, t, torch.zeros_like(t))
+    del chs, prev, same, lo, hi, uu, t, order
+    cid = torch.where(torch.rand(r, generator=g, device=dev) < mark_frac,
+                      torch.randint(1, 256, (r,), generator=g, device=dev), torch.zeros(r, dtype=torch.int64, device=dev)).to(torch.uint8)
+    rows = torch.empty((r, 18), dtype=torch.uint8, device=dev)
+    rows[:, 0] = ch
+    for b in range(5):
+        rows[:, 1 + b] = ((idx >> (8 * b)) & 255).to(torch.uint8)
+        rows[:, 13 + b] = ((thr >> (8 * b)) & 255).to(torch.uint8)
+    for b in range(4):
+        rows[:, 6 + b] = ((dest >> (8 * b)) & 255).to(torch.uint8)
+    rows[:, 10] = (doff & 255).to(torch.uint8)
+    rows[:, 11] = ((doff >> 8) & 255).to(torch.uint8)
+    rows[:, 12] = cid
+    return rows, n, {"ch": ch, "lens": lens, "dest": dest, "doff": doff}
+
+
+def walk_reads(cols: dict, n_reads: int, read_len: int, *, sub: float = 0.01, seed: int = 6, chunk_reads: int = 1 << 21):
+    """Reads that spell LF walks of a move table (so they match it except at the injected substitutions): start at a
+    random (row, offset), emit the row character, step LF (LF_table.hpp:251-262), repeat; the walk runs right to left,
+    so the emitted characters are reversed.  Walks that hit the terminator row keep going (its byte 1 becomes 'A').
+    Returns host numpy (seqs u8, offsets u64)."""
+    ch, lens, dest, doff = cols["ch"], cols["lens"], cols["dest"], cols["doff"]
+    dev = ch.device
+    r = ch.numel()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = np.empty(n_reads * read_len, dtype=np.uint8)
+    acgt = torch.tensor([ord(x) for x in "ACGT"], dtype=torch.uint8, device=dev)
+    for a in range(0, n_reads, chunk_reads):
+        m = min(chunk_reads, n_reads - a)
+        k = torch.randint(0, r, (m,), generator=g, device=dev)
+        o = (torch.rand(m, generator=g, device=dev, dtype=torch.float64) * lens[k].to(torch.float64)).to(torch.int64)
+        buf = torch.empty((m, read_len), dtype=torch.uint8, device=dev)
+        for j in range(read_len - 1, -1, -1):
+            c = ch[k]
+            buf[:, j] = torch.where(c <= 1, acgt[0].expand_as(c), c)
+            o = doff[k] + o
+            k = dest[k]
+            while True:
+                over = o >= lens[k]
+                if not bool(over.any()):
+                    break
+                o = torch.where(over, o - lens[k], o)
+                k = torch.where(over, k + 1, k)
+        if sub > 0:
+            hit = torch.rand((m, read_len), generator=g, device=dev) < sub
+            rot = torch.randint(1, 4, (m, read_len), generator=g, device=dev)
+            code = ((buf >> 1) & 3).to(torch.int64)                     # A0 C1 T2 G3
+            lut = torch.tensor([ord(x) for x in "ACTG"], dtype=torch.uint8, device=dev)
+            buf = torch.where(hit, lut[(code + rot) & 3], buf)
+        out[a * read_len:(a + m) * read_len] = buf.reshape(-1).cpu().numpy()
+    offsets = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len))
+    return out, offsets

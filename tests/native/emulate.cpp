@@ -123,15 +123,14 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
         ReadMeta m{off[i], (uint32_t)len, packed ? 0u : (uint32_t)off[i]};
         auto run = [&](auto &L, auto packed_tag) {
             constexpr bool P = decltype(packed_tag)::value;
-            Policies pol;
-            lane_begin<P, 0>(L, t->view, bv, m, pol);
+            lane_begin<P>(L, t->view, bv, m);
             while (L.state != LANE_IDLE) {
                 if (narrow) {
                     const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t->view.cold : t->view.hot;
-                    lane_step_narrow<P, 0>(L, t->view, bv, base[L.addr], t->code_lut, pol);
+                    lane_step_narrow<P>(L, t->view, bv, base[L.addr], t->code_lut);
                 } else {
                     if (g_trace_on) g_trace.push_back(L.addr);
-                    lane_step<P, 0>(L, t->view, bv, ld_row<0>(t->view.rows + L.addr, pol), t->code_lut, pol);
+                    lane_step<P>(L, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
                 }
                 ++iters;
             }
