@@ -213,9 +213,39 @@ struct ReadMeta {           // 16 bytes per read
     uint32_t in_off;        // packed reads: 32-bit word index into words[]; byte reads: byte index into bytes[]
 };
 
+// Long reads are cut into chunk tasks so that one read's serial chain does not bound the whole batch.  A read is
+// traversed right to left, so chunk 0 is the top chunk [hi0=len .. lo0) and starts from the true initial state; every
+// other chunk starts SPECULATIVELY from the initial state `warm` bases above its range (top = hi + warm), runs the
+// warm-up without emitting, and records the state in which it arrives at base hi-1.  After the main pass, the chain
+// of a read is verified top-down (fixup_chain): a chunk whose recorded arrival state equals the true state left by
+// the chunk above it is exact as it stands (states merge at reposition jumps, so a few hundred noisy bases are
+// enough); any other chunk is re-traversed from the true state by one lane.  The result is bit-identical to the
+// serial traversal whatever the warm-up length; the warm-up only decides how often the re-traversal is needed.
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+struct ChunkTask {          // 32 bytes
+    uint64_t out_off;       // index of base 0 of the READ in pml[] / cid[]
+    uint32_t in_off;        // the read's first word (packed) or byte
+    uint32_t lo, hi;        // bases [lo, hi) are emitted by this task
+    uint32_t top;           // bases [hi, top) are the warm-up (top == hi for the first chunk of a read)
+    uint32_t slot;          // index of this chunk's ChainState records
+    uint32_t len;           // top - lo: work in this task (sort key)
+};
+struct ChainState {         // traversal state just before a base is consumed
+    uint32_t row, off, plen, pad;
+};
+struct ChainDesc {          // one split read: its chunk tasks occupy slots [first_slot, first_slot + n_chunks), top chunk first
+    uint32_t first_slot, n_chunks, packed, pad;
+};
+
 struct BatchView {
-    const ReadMeta *meta;   // n_packed entries, input order; reads shipped as bytes have len = 0 here
+    const ReadMeta *meta;   // n_packed entries, input order; reads shipped as bytes (or split into tasks) have len = 0 here
     const ReadMeta *meta_b; // n_bytes entries: the reads that contain something outside ACGT
+    const ChunkTask *tasks;     // n_tasks + n_tasks_b chunk tasks in scheduling order (packed ones first)
+    const ChunkTask *by_slot;   // the same tasks indexed by slot (for fixup_chain)
+    ChainState *start_state;    // [slots] state recorded on arrival at base hi-1
+    ChainState *end_state;      // [slots] state after base lo was consumed
+    const ChainDesc *chains;    // n_chains split reads
+    uint32_t n_tasks, n_tasks_b, n_chains, pad;
     const uint32_t *words;  // 2 bit per base, 16 bases per word, base j of a read at bits 2*(j&15) of word j>>4
     const uint8_t *bytes;   // raw bytes of the reads that contain something outside ACGT
     void *pml;              // PmlT[total bases]
@@ -237,6 +267,9 @@ template <typename PmlT> struct Lane {
     uint32_t plen = 0;      // current pseudo matching length
     uint32_t j = 0;         // bases still to process; the next base is j-1 (right to left, col_bwt.hpp:512)
     uint32_t in_off = 0;
+    uint32_t j_stop = 0;    // stop after base j_stop (0 for whole reads, lo for chunk tasks)
+    uint32_t emit_top = 0;  // bases >= emit_top are warm-up: traversed, not emitted
+    uint32_t slot = NO_SLOT;
     uint32_t rw = 0;        // current packed word
     uint64_t out_base = 0;
     uint32_t cnt = 0;       // staged outputs
@@ -284,7 +317,7 @@ template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &b
     L.cnt = 0;
 }
 
-template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)
+template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)   // jj < emit_top
 {
     const uint64_t g = L.out_base + jj;
     L.accc[1] = (L.accc[1] << 8) | (L.accc[0] >> 24);
@@ -301,7 +334,7 @@ template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv
         reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
     }
     ++L.cnt;
-    if ((g & 7) == 0 || jj == 0) lane_flush(L, bv, g);
+    if ((g & 7) == 0 || jj == L.j_stop) lane_flush(L, bv, g);
 }
 
 // Start read `m` on this lane (zero-length reads are skipped by the caller).
@@ -312,10 +345,48 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const
     L.off = t.last_len - 1;         // col_bwt.hpp:505
     L.plen = 0;
     L.j = m.len;
+    L.j_stop = 0;
+    L.emit_top = m.len;
+    L.slot = NO_SLOT;
     L.in_off = m.in_off;
     L.out_base = m.out_off;
     L.cnt = 0;
     if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
+}
+
+// Start a chunk task: from the initial state at base top-1 (speculative unless top is the read length) ...
+template <bool PACKED, typename PmlT> CB_HD void lane_begin_task(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const ChunkTask &k)
+{
+    L.state = LANE_LF;
+    L.addr = t.r - 1;
+    L.off = t.last_len - 1;
+    L.plen = 0;
+    L.j = k.top;
+    L.j_stop = k.lo;
+    L.emit_top = k.hi;
+    L.slot = k.slot;
+    L.in_off = k.in_off;
+    L.out_base = k.out_off;
+    L.cnt = 0;
+    if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.top - 1) >> 4));
+}
+
+// ... or from a known state at base hi-1 (re-traversal of a chunk whose speculation failed).
+template <bool PACKED, typename PmlT>
+CB_HD void lane_begin_from_state(Lane<PmlT> &L, const BatchView &bv, const ChunkTask &k, const ChainState &s)
+{
+    L.state = LANE_LF;
+    L.addr = s.row;
+    L.off = s.off;
+    L.plen = s.plen;
+    L.j = k.hi;
+    L.j_stop = k.lo;
+    L.emit_top = k.hi;
+    L.slot = k.slot;
+    L.in_off = k.in_off;
+    L.out_base = k.out_off;
+    L.cnt = 0;
+    if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.hi - 1) >> 4));
 }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
@@ -336,7 +407,16 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
         ++L.addr;
         return;
     }
-    // settled on (addr, off): process the next base
+    // settled on (addr, off)
+    if (L.slot != NO_SLOT) {
+        if (L.j == L.emit_top) bv.start_state[L.slot] = ChainState{L.addr, L.off, L.plen, 0};   // arrival at base hi-1
+        if (L.j == L.j_stop) {                                                                   // base lo consumed and stepped
+            bv.end_state[L.slot] = ChainState{L.addr, L.off, L.plen, 0};
+            L.state = LANE_IDLE;
+            return;
+        }
+    }
+    // process the next base
     const uint32_t jj = --L.j;
     uint32_t code;
     uint8_t cbyte = 0;
@@ -357,8 +437,8 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     } else {
         L.plen = 0;                              // col_bwt.hpp:520-523
     }
-    lane_emit(L, bv, jj, L.plen, cid);
-    if (jj == 0) {                               // the reference's last LF step has no observable effect
+    if (jj < L.emit_top) lane_emit(L, bv, jj, L.plen, cid);
+    if (jj == L.j_stop && L.slot == NO_SLOT) {   // whole read: the reference's last LF step has no observable effect
         L.state = LANE_IDLE;
         return;
     }
@@ -369,10 +449,18 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
             const uint64_t meta = row_meta(row);
             const uint32_t slot = (code - chc - 1u) & 3u;
             const uint32_t mode = (uint32_t)(meta >> (11 + 2 * slot)) & 3u;
+            const uint32_t d = (uint32_t)(meta >> (17 + 10 * slot)) & 1023u;
             if (mode == 3) {
-                found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+                if (chc != CHC_OTHER && (d & 31u) && (d >> 5)) {
+                    // both neighbours are known, only the in-row flip offset did not fit (a second threshold inside this
+                    // row): evaluate `pos < thr[succ]` (col_bwt.hpp:560) directly -- two loads instead of a search
+                    use_pred = ld_ro(t.idx + L.addr) + L.off < ld_ro(t.thr + L.addr + (d >> 5));
+                    tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
+                    found = true;
+                } else {
+                    found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+                }
             } else {
-                const uint32_t d = (uint32_t)(meta >> (17 + 10 * slot)) & 1023u;
                 const uint32_t fx = (uint32_t)(meta >> 47) & 0xFFFFu;
                 use_pred = (mode == 1) || (mode == 2 && L.off < fx);
                 tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
@@ -404,10 +492,16 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
         const uint32_t mode = (uint32_t)(w >> (2 * slot)) & 3u;
         bool found, use_pred = false;
         uint32_t tgt = 0;
+        const uint32_t d = (uint32_t)(w >> (6 + 10 * slot)) & 1023u;
         if (mode == 3) {
-            found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+            if ((d & 31u) && (d >> 5)) {   // second threshold inside this row: exact compare, see lane_step
+                use_pred = ld_ro(t.idx + L.addr) + L.off < ld_ro(t.thr + L.addr + (d >> 5));
+                tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
+                found = true;
+            } else {
+                found = slow_reposition(t, L.addr, L.off, primary_byte((int)code), &tgt, &use_pred);
+            }
         } else {
-            const uint32_t d = (uint32_t)(w >> (6 + 10 * slot)) & 1023u;
             const uint32_t fx = (uint32_t)(w >> 36) & 0xFFFFu;
             use_pred = (mode == 1) || (mode == 2 && L.off < fx);
             tgt = use_pred ? L.addr - (d & 31u) : L.addr + (d >> 5);
@@ -440,6 +534,14 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
         ++L.addr;
         return;
     }
+    if (L.slot != NO_SLOT) {
+        if (L.j == L.emit_top) bv.start_state[L.slot] = ChainState{L.addr, L.off, L.plen, 0};
+        if (L.j == L.j_stop) {
+            bv.end_state[L.slot] = ChainState{L.addr, L.off, L.plen, 0};
+            L.state = LANE_IDLE;
+            return;
+        }
+    }
     const uint32_t jj = --L.j;
     uint32_t code;
     uint8_t cbyte = 0;
@@ -454,8 +556,8 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
     if (!PACKED && code >= CODE_OTHER)
         match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
     L.plen = match ? L.plen + 1 : 0;
-    lane_emit(L, bv, jj, L.plen, cid);
-    if (jj == 0) {
+    if (jj < L.emit_top) lane_emit(L, bv, jj, L.plen, cid);
+    if (jj == L.j_stop && L.slot == NO_SLOT) {
         L.state = LANE_IDLE;
         return;
     }
@@ -476,6 +578,55 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
     }
     L.off = doff + L.off;
     L.addr = dest;
+}
+
+
+// Run a lane to completion on its own (fixup re-traversal on the device, every lane in the host emulation).
+template <bool PACKED, bool NARROW, typename PmlT>
+CB_HD void lane_run(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint8_t *code_lut)
+{
+    while (L.state != LANE_IDLE) {
+        if (NARROW) {
+            const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
+            lane_step_narrow<PACKED>(L, t, bv, ld_row64(base + L.addr), code_lut);
+        } else {
+            lane_step<PACKED>(L, t, bv, ld_row(t.rows + L.addr), code_lut);
+        }
+    }
+}
+
+// Verify / repair the chunk chain of one split read, top chunk first (see ChunkTask).  Returns the number of chunks
+// that had to be re-traversed.
+template <bool PACKED, bool NARROW, typename PmlT>
+CB_HD uint32_t fixup_chain(const TableView &t, const BatchView &bv, const ChainDesc &c, const uint8_t *code_lut)
+{
+    uint32_t redone = 0;
+    PmlT *pml = reinterpret_cast<PmlT *>(bv.pml);
+    for (uint32_t i = 1; i < c.n_chunks; ++i) {
+        const uint32_t slot = c.first_slot + i;
+        const ChainState truth = bv.end_state[slot - 1];          // exact by induction (chunk 0 starts from the true state)
+        const ChainState spec = bv.start_state[slot];
+        const ChunkTask k = bv.by_slot[slot];
+        if (spec.row == truth.row && spec.off == truth.off) {
+            // same position: everything below is identical except that the running match length may have started
+            // before the warm-up window; shift it until the first mismatch of the chunk
+            const uint32_t delta = truth.plen - spec.plen;
+            if (delta != 0) {
+                uint32_t j = k.hi;
+                while (j > k.lo && pml[k.out_off + j - 1] != 0) {
+                    pml[k.out_off + j - 1] = (PmlT)(pml[k.out_off + j - 1] + delta);
+                    --j;
+                }
+                if (j == k.lo) bv.end_state[slot].plen += delta;  // no mismatch in the whole chunk: carry on
+            }
+        } else {
+            Lane<PmlT> L;
+            lane_begin_from_state<PACKED>(L, bv, k, truth);
+            lane_run<PACKED, NARROW>(L, t, bv, code_lut);
+            ++redone;
+        }
+    }
+    return redone;
 }
 
 } // namespace colbwt

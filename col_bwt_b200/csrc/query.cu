@@ -17,6 +17,7 @@
 #include <thread>
 
 #include "internal.h"
+#include "tasks.h"
 
 namespace colbwt {
 
@@ -116,13 +117,14 @@ struct Staging {
     uint64_t n_reads = 0, n_words = 0, n_irregular = 0, n_byte_bases = 0, n_bases = 0;
     uint32_t max_len = 0;
     bool sorted = false;
+    TaskPlan plan;                // chunk tasks of the long reads that were split (empty for short-read batches)
 };
 
 static inline uint64_t words_of(uint64_t len) { return (len + 15) >> 4; }
 
 // Reads [r0, r1) of (seqs, off).  Output offsets are relative to off[r0].  Staging arrays must hold
 // (r1-r0) metas (x2), sum(words_of(len)) words and up to n_bases bytes.
-static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t seq_end, Staging &st)
+static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t seq_end, uint64_t lanes, Staging &st)
 {
     Pool &pool = Pool::get();
     const uint64_t n_reads = r1 - r0, base0 = off[r0], n_bases = off[r1] - base0;
@@ -166,12 +168,6 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
     }
     st.n_irregular = icount[T];
     st.n_byte_bases = ibases[T];
-    // Lanes take reads in meta order (global cursor): with reads of very different lengths, start the longest first so
-    // that the last lanes to finish are working on short reads, not on a 100 kbp one.
-    if (st.max_len >= 1024 && n_reads > 1 && (uint64_t)st.max_len * n_reads > 2 * n_bases) {
-        std::sort(st.meta, st.meta + n_reads, [](const ReadMeta &a, const ReadMeta &b) { return a.len > b.len; });
-        st.sorted = true;
-    }
     if (st.n_irregular) {
         pool.parallel_for(T, [&](int t) {
             uint64_t k = icount[t], b = ibases[t];
@@ -183,6 +179,79 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
             }
         });
     }
+    // Long reads: cut into chunk tasks when one read's serial chain would dominate the batch (tasks.h).
+    st.plan.clear();
+    const SplitParams sp = SplitParams::from_env();   // read per call: tests switch it with the environment
+    if (sp.wanted(st.max_len, n_bases, lanes)) {
+        for (uint64_t i = 0; i < n_reads; ++i)
+            if (st.meta[i].len >= sp.min_len) {
+                st.plan.add_read(st.meta[i].out_off, st.meta[i].in_off, st.meta[i].len, true, sp);
+                st.meta[i].len = 0;
+            }
+        for (uint64_t i = 0; i < st.n_irregular; ++i)
+            if (st.meta_b[i].len >= sp.min_len) {
+                st.plan.add_read(st.meta_b[i].out_off, st.meta_b[i].in_off, st.meta_b[i].len, false, sp);
+                st.meta_b[i].len = 0;
+            }
+        st.plan.finish();
+    }
+    // Lanes take reads in meta order (global cursor): with reads of very different lengths, start the longest first so
+    // that the last lanes to finish are working on short reads, not on a 100 kbp one.
+    if (st.max_len >= 1024 && n_reads > 1 && (uint64_t)st.max_len * n_reads > 2 * n_bases) {
+        std::sort(st.meta, st.meta + n_reads, [](const ReadMeta &a, const ReadMeta &b) { return a.len > b.len; });
+        st.sorted = true;
+    }
+}
+
+// Device copies of a TaskPlan (grown on demand, reused between chunks / calls).
+struct DevicePlan {
+    ChunkTask *tasks = nullptr, *by_slot = nullptr;
+    ChainState *start_state = nullptr, *end_state = nullptr;
+    ChainDesc *chains = nullptr;
+    size_t cap_tasks = 0, cap_chains = 0;
+    void release()
+    {
+        cudaFree(tasks);
+        cudaFree(by_slot);
+        cudaFree(start_state);
+        cudaFree(end_state);
+        cudaFree(chains);
+        *this = DevicePlan{};
+    }
+};
+
+static int upload_plan(const TaskPlan &plan, DevicePlan &dp, BatchView &bv, cudaStream_t stream)
+{
+    bv.n_tasks = plan.n_tasks;
+    bv.n_tasks_b = plan.n_tasks_b;
+    bv.n_chains = (uint32_t)plan.chains.size();
+    if (plan.by_slot.empty()) {
+        bv.tasks = bv.by_slot = nullptr;
+        bv.start_state = bv.end_state = nullptr;
+        bv.chains = nullptr;
+        return COLBWT_OK;
+    }
+    const size_t nt = plan.by_slot.size(), nc = plan.chains.size();
+    if (nt > dp.cap_tasks || nc > dp.cap_chains) {
+        CB_CUDA(cudaStreamSynchronize(stream));
+        dp.release();
+        dp.cap_tasks = nt + nt / 4 + 64;
+        dp.cap_chains = nc + nc / 4 + 64;
+        CB_CUDA(cudaMalloc(&dp.tasks, dp.cap_tasks * sizeof(ChunkTask)));
+        CB_CUDA(cudaMalloc(&dp.by_slot, dp.cap_tasks * sizeof(ChunkTask)));
+        CB_CUDA(cudaMalloc(&dp.start_state, dp.cap_tasks * sizeof(ChainState)));
+        CB_CUDA(cudaMalloc(&dp.end_state, dp.cap_tasks * sizeof(ChainState)));
+        CB_CUDA(cudaMalloc(&dp.chains, dp.cap_chains * sizeof(ChainDesc)));
+    }
+    CB_CUDA(cudaMemcpyAsync(dp.tasks, plan.tasks.data(), nt * sizeof(ChunkTask), cudaMemcpyHostToDevice, stream));
+    CB_CUDA(cudaMemcpyAsync(dp.by_slot, plan.by_slot.data(), nt * sizeof(ChunkTask), cudaMemcpyHostToDevice, stream));
+    CB_CUDA(cudaMemcpyAsync(dp.chains, plan.chains.data(), nc * sizeof(ChainDesc), cudaMemcpyHostToDevice, stream));
+    bv.tasks = dp.tasks;
+    bv.by_slot = dp.by_slot;
+    bv.start_state = dp.start_state;
+    bv.end_state = dp.end_state;
+    bv.chains = dp.chains;
+    return COLBWT_OK;
 }
 
 } // namespace colbwt
@@ -202,6 +271,7 @@ struct colbwt_batch {
     uint64_t n_bases = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DevicePlan plan;
 };
 
 static int check_width(int pml_width, uint32_t max_len)
@@ -232,6 +302,7 @@ extern "C" void colbwt_batch_free(colbwt_batch *b)
     cudaFree(b->d_pml);
     cudaFree(b->d_cid);
     cudaFree(b->d_cursors);
+    b->plan.release();
     if (b->e0) cudaEventDestroy(b->e0);
     if (b->e1) cudaEventDestroy(b->e1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -272,7 +343,7 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     st.meta_b = meta_b.data();
     st.words = words.data();
     st.bytes = bytes.data();
-    prepare_reads(seqs, off, 0, n_reads, off[n_reads], st);
+    prepare_reads(seqs, off, 0, n_reads, off[n_reads], (uint64_t)dt.sm_count * 1024, st);
     if (int rc = check_width(pml_width, st.max_len)) return rc;
     if (st.n_byte_bases >= (1ull << 32)) {
         set_error("colbwt_batch_upload: more than 4 Gi bases of irregular reads in one batch; split it");
@@ -288,7 +359,7 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     CB_CUDA(cudaMalloc(&b->d_bytes, std::max<uint64_t>(16, st.n_byte_bases)));
     CB_CUDA(cudaMalloc(&b->d_pml, (n_bases + 8) * (uint64_t)pml_width));
     CB_CUDA(cudaMalloc(&b->d_cid, n_bases + 8));
-    CB_CUDA(cudaMalloc(&b->d_cursors, 2 * sizeof(unsigned long long)));
+    CB_CUDA(cudaMalloc(&b->d_cursors, 4 * sizeof(unsigned long long)));
     CB_CUDA(cudaMemcpy(b->d_meta, meta.data(), n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice));
     CB_CUDA(cudaMemcpy(b->d_meta_b, meta_b.data(), st.n_irregular * sizeof(ReadMeta), cudaMemcpyHostToDevice));
     CB_CUDA(cudaMemcpy(b->d_words, words.data(), n_words * 4, cudaMemcpyHostToDevice));
@@ -301,6 +372,8 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     b->view.cid = (uint8_t *)b->d_cid;
     b->view.n_packed = (uint32_t)n_reads;
     b->view.n_bytes = (uint32_t)st.n_irregular;
+    if (int rc = upload_plan(st.plan, b->plan, b->view, b->stream)) return rc;
+    CB_CUDA(cudaStreamSynchronize(b->stream));
     *out = b.release();
     return COLBWT_OK;
 }
@@ -308,7 +381,7 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
 extern "C" int colbwt_batch_launches(const colbwt_batch *b)
 {
     if (!b) return 0;
-    return (b->view.n_packed ? 1 : 0) + (b->view.n_bytes ? 1 : 0);
+    return ((b->view.n_packed || b->view.n_tasks) ? 1 : 0) + ((b->view.n_bytes || b->view.n_tasks_b) ? 1 : 0) + (b->view.n_chains ? 1 : 0);
 }
 
 extern "C" int colbwt_batch_run(colbwt_batch *b, int iters, float *ms_per_iter)
@@ -373,6 +446,7 @@ struct Slot {
     uint32_t *d_words = nullptr;
     uint8_t *d_bytes = nullptr, *d_pml = nullptr, *d_cid = nullptr;
     unsigned long long *d_cursors = nullptr;
+    DevicePlan plan;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};   // COLBWT_TRACE=2: H2D start / kernel start / D2H start / end
@@ -404,6 +478,7 @@ struct Pipeline {
             cudaFree(k.d_pml);
             cudaFree(k.d_cid);
             cudaFree(k.d_cursors);
+            k.plan.release();
             if (k.done) cudaEventDestroy(k.done);
             for (auto e : k.tev) if (e) cudaEventDestroy(e);
             if (k.stream) cudaStreamDestroy(k.stream);
@@ -456,7 +531,7 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
         CB_CUDA(cudaMalloc(&k.d_bytes, chunk_bases + 16));
         CB_CUDA(cudaMalloc(&k.d_pml, (chunk_bases + 8) * (uint64_t)pml_width));
         CB_CUDA(cudaMalloc(&k.d_cid, chunk_bases + 8));
-        CB_CUDA(cudaMalloc(&k.d_cursors, 2 * sizeof(unsigned long long)));
+        CB_CUDA(cudaMalloc(&k.d_cursors, 4 * sizeof(unsigned long long)));
         CB_CUDA(cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking));
         CB_CUDA(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
         for (auto &e : k.tev) CB_CUDA(cudaEventCreate(&e));
@@ -483,6 +558,10 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     uint32_t max_len = 0;
     for (uint64_t i = 0; i < n_reads; ++i) max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
     if (int rc = check_width(pml_width, max_len)) return rc;
+    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read at a time and
+    // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
+    if (!getenv("COLBWT_CHUNK_BASES"))
+        chunk_bases = std::max<uint64_t>(chunk_bases, std::min<uint64_t>(512ull << 20, (total_bases / n_reads) * 32768));
     chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
     chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
     // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
@@ -547,7 +626,7 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         st.meta_b = k.h_meta_b;
         st.words = k.h_words;
         st.bytes = k.h_bytes;
-        prepare_reads(seqs, off, r0, r1, off[n_reads], st);
+        prepare_reads(seqs, off, r0, r1, off[n_reads], (uint64_t)dt.sm_count * 1024 / (uint64_t)std::min<int>(SLOTS_PER_DEVICE, 4), st);
         t_pack += now() - t0;
         t0 = now();
 

@@ -1,0 +1,79 @@
+// tasks.h -- host-side planning of chunk tasks for long reads (see ChunkTask in colbwt_core.cuh).  Shared by the
+// driver (query.cu) and the host emulation used by the CPU tests.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "colbwt_core.cuh"
+
+namespace colbwt {
+
+struct SplitParams {
+    uint32_t min_len = 8192;   // reads at least this long are split ...
+    uint32_t chunk = 4096;     // ... into chunks of about this many bases ...
+    uint32_t warm = 512;       // ... each started this many bases early from the initial state
+    int mode = -1;             // -1 auto (split when the longest read would dominate the batch), 0 never, 1 always
+    static SplitParams from_env()
+    {
+        SplitParams p;
+        if (const char *e = getenv("COLBWT_SPLIT")) p.mode = atoi(e);
+        if (const char *e = getenv("COLBWT_SPLIT_CHUNK")) p.chunk = std::max(8, atoi(e));
+        if (const char *e = getenv("COLBWT_SPLIT_WARM")) p.warm = std::max(0, atoi(e));
+        if (const char *e = getenv("COLBWT_SPLIT_MIN")) p.min_len = std::max(16, atoi(e));
+        p.min_len = std::max(p.min_len, 2 * p.chunk);
+        return p;
+    }
+    // `lanes` reads are in flight at a time; splitting pays when one read's serial chain is a large share of the
+    // time the whole batch would need at full parallelism.
+    bool wanted(uint64_t max_len, uint64_t total_bases, uint64_t lanes) const
+    {
+        if (mode == 0 || max_len < min_len) return false;
+        if (mode == 1) return true;
+        return max_len * lanes > total_bases / 4;
+    }
+};
+
+struct TaskPlan {
+    std::vector<ChunkTask> tasks;     // scheduling order: packed tasks (longest first), then byte tasks (longest first)
+    std::vector<ChunkTask> by_slot;   // slot order
+    std::vector<ChainDesc> chains;
+    uint32_t n_tasks = 0, n_tasks_b = 0;
+    void clear()
+    {
+        tasks.clear();
+        by_slot.clear();
+        chains.clear();
+        n_tasks = n_tasks_b = 0;
+    }
+    // Cut one read into chunk tasks, top chunk first.
+    void add_read(uint64_t out_off, uint32_t in_off, uint32_t len, bool packed, const SplitParams &sp)
+    {
+        const uint32_t k = (len + sp.chunk - 1) / sp.chunk;
+        const uint32_t size = (len + k - 1) / k;
+        ChainDesc c{(uint32_t)by_slot.size(), 0, packed ? 1u : 0u, 0};
+        for (uint32_t hi = len; hi > 0;) {
+            const uint32_t lo = hi > size ? hi - size : 0;
+            const uint32_t top = (hi == len) ? hi : std::min<uint32_t>(len, hi + sp.warm);
+            by_slot.push_back(ChunkTask{out_off, in_off, lo, hi, top, (uint32_t)by_slot.size(), top - lo});
+            ++c.n_chunks;
+            hi = lo;
+        }
+        chains.push_back(c);
+    }
+    void finish()
+    {
+        std::vector<ChunkTask> p, b;
+        for (const ChainDesc &c : chains)
+            for (uint32_t i = 0; i < c.n_chunks; ++i) (c.packed ? p : b).push_back(by_slot[c.first_slot + i]);
+        auto longer = [](const ChunkTask &x, const ChunkTask &y) { return x.len > y.len; };
+        std::stable_sort(p.begin(), p.end(), longer);
+        std::stable_sort(b.begin(), b.end(), longer);
+        n_tasks = (uint32_t)p.size();
+        n_tasks_b = (uint32_t)b.size();
+        tasks = std::move(p);
+        tasks.insert(tasks.end(), b.begin(), b.end());
+    }
+};
+
+} // namespace colbwt

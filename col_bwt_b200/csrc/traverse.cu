@@ -27,7 +27,9 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     }
     const uint32_t lane = threadIdx.x & 31;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
-    const uint32_t count = PACKED ? bv.n_packed : bv.n_bytes;
+    const ChunkTask *tasks = PACKED ? bv.tasks : bv.tasks + bv.n_tasks;
+    const uint32_t n_tasks = PACKED ? bv.n_tasks : bv.n_tasks_b;       // chunk tasks of split reads go first (longest work)
+    const uint64_t count = (uint64_t)n_tasks + (PACKED ? bv.n_packed : bv.n_bytes);
     Lane<PmlT> L;
     bool exhausted = false;
     for (;;) {
@@ -40,13 +42,18 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want & (1u << lane)) {
                 const unsigned long long i = base + __popc(want & ((1u << lane) - 1u));
-                if (i < count) {
-                    const uint4 mv = __ldg(reinterpret_cast<const uint4 *>(meta + i));
+                if (i < n_tasks) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(tasks + i));
+                    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(tasks + i) + 1);
+                    const ChunkTask k{(uint64_t)a.x | ((uint64_t)a.y << 32), a.z, a.w, b.x, b.y, b.z, b.w};
+                    lane_begin_task<PACKED>(L, t, bv, k);
+                } else if (i < count) {
+                    const uint4 mv = __ldg(reinterpret_cast<const uint4 *>(meta + (i - n_tasks)));
                     ReadMeta m;
                     m.out_off = (uint64_t)mv.x | ((uint64_t)mv.y << 32);
                     m.len = mv.z;
                     m.in_off = mv.w;
-                    if (m.len) lane_begin<PACKED>(L, t, bv, m);   // zero-length read: nothing to emit
+                    if (m.len) lane_begin<PACKED>(L, t, bv, m);   // zero-length / irregular / split read: nothing to do here
                 } else {
                     exhausted = true;
                 }
@@ -67,6 +74,20 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     }
 }
 
+// One lane per split read: verify its chunk chain, re-traverse the chunks whose speculative start did not converge.
+template <typename PmlT, bool NARROW>
+__global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *redone)
+{
+    __shared__ uint8_t code_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) code_lut[i] = code_lut_g[i];
+    __syncthreads();
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= bv.n_chains) return;
+    const ChainDesc d = bv.chains[c];
+    const uint32_t n = d.packed ? fixup_chain<true, NARROW, PmlT>(t, bv, d, code_lut) : fixup_chain<false, NARROW, PmlT>(t, bv, d, code_lut);
+    if (n) atomicAdd(redone, (unsigned long long)n);
+}
+
 // CTAs per SM: 4 (1024 lanes per SM, 48 registers, no spills) is the measured optimum on DRAM-resident tables -- more
 // lanes in flight only thrash the L2 (profiles/r1/variant_sweep2.log); COLBWT_CTAS=8 selects the full-occupancy build.
 template <bool PACKED, typename PmlT>
@@ -74,7 +95,7 @@ static void launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, cons
                        unsigned long long *cursor, cudaStream_t stream)
 {
     static const int ctas = (getenv("COLBWT_CTAS") && atoi(getenv("COLBWT_CTAS")) == 8) ? 8 : 4;
-    const uint64_t need = ((uint64_t)reads + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
+    const uint64_t need = ((uint64_t)reads + (PACKED ? bv.n_tasks : bv.n_tasks_b) + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
     const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
     if (ctas == 8) {
@@ -88,19 +109,34 @@ static void launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, cons
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)
 {
-    // two cursors: [0] packed reads, [1] byte reads
-    CB_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned long long), stream));
+    // [0] cursor of the packed work list, [1] of the byte work list, [2] chunks re-traversed by k_fixup
+    CB_CUDA(cudaMemsetAsync(d_cursors, 0, 3 * sizeof(unsigned long long), stream));
     const uint8_t *lut = (const uint8_t *)dt.d_code_lut;
-    if (bv.n_packed) {
+    if (bv.n_packed || bv.n_tasks) {
         if (pml_width == 2) launch_one<true, uint16_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         else if (pml_width == 1) launch_one<true, uint8_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         else launch_one<true, uint32_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         CB_CUDA(cudaGetLastError());
     }
-    if (bv.n_bytes) {
+    if (bv.n_bytes || bv.n_tasks_b) {
         if (pml_width == 2) launch_one<false, uint16_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         else if (pml_width == 1) launch_one<false, uint8_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         else launch_one<false, uint32_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        CB_CUDA(cudaGetLastError());
+    }
+    if (bv.n_chains) {   // split reads exist: verify / repair their chunk chains (d_cursors[2] counts re-traversed chunks)
+        const unsigned grid = (bv.n_chains + 127) / 128;
+        const bool narrow = dt.view.hot != nullptr;
+        if (pml_width == 2) {
+            if (narrow) k_fixup<uint16_t, true><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+            else k_fixup<uint16_t, false><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+        } else if (pml_width == 4) {
+            if (narrow) k_fixup<uint32_t, true><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+            else k_fixup<uint32_t, false><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+        } else {
+            if (narrow) k_fixup<uint8_t, true><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+            else k_fixup<uint8_t, false><<<grid, 128, 0, stream>>>(dt.view, bv, lut, d_cursors + 2);
+        }
         CB_CUDA(cudaGetLastError());
     }
     return COLBWT_OK;

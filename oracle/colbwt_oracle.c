@@ -161,6 +161,25 @@ void oracle_query(const oracle_table *t, const uint8_t *pattern, uint64_t m, uin
     }
 }
 
+/* Experiment support: like oracle_query, and also records the state (row, offset) the traversal is in just before it
+ * consumes base j (so state[m-1] is the initial state). */
+void oracle_query_states(const oracle_table *t, const uint8_t *pattern, uint64_t m, uint32_t *pml, uint32_t *row_out, uint32_t *off_out)
+{
+    uint64_t pos = t->n - 1, interval = t->r - 1, offset = row_len(t, interval) - 1, length = 0;
+    for (uint64_t i = 0; i < m; ++i) {
+        const uint64_t j = m - i - 1;
+        uint8_t c = pattern[j];
+        row_out[j] = (uint32_t)interval;
+        off_out[j] = (uint32_t)offset;
+        if (t->ch[interval] == c) ++length;
+        else { length = 0; threshold_step(t, &interval, &offset, pos, c); }
+        pml[j] = (uint32_t)length;
+        uint64_t ni = t->interval[interval], no = (uint64_t)t->offset[interval] + offset;
+        while (no >= row_len(t, ni)) no -= row_len(t, ni++);
+        interval = ni; offset = no; pos = t->idx[interval] + offset;
+    }
+}
+
 uint64_t oracle_query_batch(const oracle_table *t, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                             uint32_t *pml, uint8_t *cid)
 {

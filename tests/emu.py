@@ -11,10 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "native", "libemulate.so")
 SRC = [os.path.join(HERE, "native", "emulate.cpp"), os.path.join(HERE, "..", "col_bwt_b200", "csrc", "pack.cpp")]
 HDR = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "colbwt_core.cuh")
+HDR2 = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "tasks.h")
 
 
 def build():
-    newest = max(os.path.getmtime(p) for p in SRC + [HDR])
+    newest = max(os.path.getmtime(p) for p in SRC + [HDR, HDR2])
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRC, check=True)
 
@@ -56,6 +57,22 @@ class Emu:
         out = np.zeros((self.r, 4), np.uint32)
         self.L.emu_rows(self.h, out.ctypes.data)
         return out
+
+    def query_split(self, seqs, offsets, chunk, warm, min_len=0, pml_width=2, narrow=False):
+        """Long-read path: chunk tasks + chain verification, as the driver plans them. Sets self.redone / self.tasks."""
+        L = self.L
+        L.emu_query_split.restype = C.c_uint64
+        L.emu_query_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        seqs = np.ascontiguousarray(seqs, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        pml = np.zeros(seqs.size + 8, {1: np.uint8, 2: np.uint16, 4: np.uint32}[pml_width])
+        cid = np.zeros(seqs.size + 8, np.uint8)
+        nt = C.c_uint64()
+        self.redone = L.emu_query_split(self.h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data, pml_width,
+                                        cid.ctypes.data, chunk, warm, min_len, int(narrow), C.byref(nt))
+        self.tasks = nt.value
+        return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]
 
     def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False):
         seqs = np.ascontiguousarray(seqs, np.uint8)

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../col_bwt_b200/csrc/colbwt_core.cuh"
+#include "../../col_bwt_b200/csrc/tasks.h"
 
 namespace colbwt {
 bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
@@ -29,6 +30,67 @@ struct EmuTable {
     uint64_t slow_rows = 0;
     uint32_t flags = 0;
 };
+
+// Long-read path: plan chunk tasks (tasks.h) exactly as the driver does, run every task as an independent lane in
+// REVERSE scheduling order (the result must not depend on the order), then verify / repair the chains (fixup_chain).
+// Returns the number of chunks that had to be re-traversed; *n_tasks_out = chunk tasks run.
+template <typename PmlT, bool NARROW>
+static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, uint8_t *cid,
+                               const SplitParams &sp, uint64_t *n_tasks_out)
+{
+    BatchView bv{};
+    bv.pml = pml;
+    bv.cid = cid;
+    bv.bytes = seqs;
+    std::vector<uint32_t> words;
+    std::vector<uint64_t> word_off(n_reads, 0);
+    std::vector<char> is_packed(n_reads, 0);
+    uint64_t nw = 0;
+    for (uint64_t i = 0; i < n_reads; ++i) { word_off[i] = nw; nw += ((off[i + 1] - off[i] + 15) >> 4); }
+    words.assign(nw + 4, 0);
+    TaskPlan plan;
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        const uint64_t len = off[i + 1] - off[i];
+        if (!len) continue;
+        is_packed[i] = pack_read_2bit(seqs + off[i], len, words.data() + word_off[i]);
+        if (len >= sp.min_len) plan.add_read(off[i], is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i], (uint32_t)len, is_packed[i], sp);
+    }
+    plan.finish();
+    std::vector<ChainState> ss(plan.by_slot.size() + 1), es(plan.by_slot.size() + 1);
+    bv.words = words.data();
+    bv.tasks = plan.tasks.data();
+    bv.by_slot = plan.by_slot.data();
+    bv.start_state = ss.data();
+    bv.end_state = es.data();
+    bv.chains = plan.chains.data();
+    bv.n_tasks = plan.n_tasks;
+    bv.n_tasks_b = plan.n_tasks_b;
+    bv.n_chains = (uint32_t)plan.chains.size();
+    for (size_t k = plan.tasks.size(); k-- > 0;) {
+        Lane<PmlT> L;
+        if (k < plan.n_tasks) {
+            lane_begin_task<true>(L, t->view, bv, plan.tasks[k]);
+            lane_run<true, NARROW>(L, t->view, bv, t->code_lut);
+        } else {
+            lane_begin_task<false>(L, t->view, bv, plan.tasks[k]);
+            lane_run<false, NARROW>(L, t->view, bv, t->code_lut);
+        }
+    }
+    for (uint64_t i = 0; i < n_reads; ++i) {   // whole reads
+        const uint64_t len = off[i + 1] - off[i];
+        if (!len || len >= sp.min_len) continue;
+        Lane<PmlT> L;
+        ReadMeta m{off[i], (uint32_t)len, is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i]};
+        if (is_packed[i]) { lane_begin<true>(L, t->view, bv, m); lane_run<true, NARROW>(L, t->view, bv, t->code_lut); }
+        else { lane_begin<false>(L, t->view, bv, m); lane_run<false, NARROW>(L, t->view, bv, t->code_lut); }
+    }
+    uint64_t redone = 0;
+    for (const ChainDesc &c : plan.chains)
+        redone += c.packed ? fixup_chain<true, NARROW, PmlT>(t->view, bv, c, t->code_lut) : fixup_chain<false, NARROW, PmlT>(t->view, bv, c, t->code_lut);
+    *n_tasks_out = plan.tasks.size();
+    return redone;
+}
+
 
 extern "C" {
 
@@ -87,6 +149,19 @@ uint64_t emu_pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t n_rea
     for (size_t k = 0; k < irr.size(); ++k) irr_out[k] = irr[k];
     return irr.size();
 }
+uint64_t emu_query_split(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid,
+                         uint32_t chunk, uint32_t warm, uint32_t min_len, int narrow, uint64_t *n_tasks_out)
+{
+    SplitParams sp;
+    sp.chunk = chunk;
+    sp.warm = warm;
+    sp.min_len = std::max(min_len, 2 * chunk);
+    sp.mode = 1;
+    if (pml_width == 1) return narrow ? emu_split_impl<uint8_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint8_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
+    if (pml_width == 2) return narrow ? emu_split_impl<uint16_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint16_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
+    return narrow ? emu_split_impl<uint32_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint32_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
+}
+
 int emu_pack(const uint8_t *seq, uint64_t len, uint32_t *words) { return pack_read_2bit(seq, len, words) ? 1 : 0; }
 uint64_t emu_slow_rows(EmuTable *t) { return t->slow_rows; }
 uint32_t emu_flags(EmuTable *t) { return t->flags; }

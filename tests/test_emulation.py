@@ -158,3 +158,47 @@ def test_slice_packer_overreads_safely_and_flags_irregular_reads():
             for j, c in enumerate(r):
                 assert (int(words[w + (j >> 4)]) >> (2 * (j & 15))) & 3 == (c >> 1) & 3
         w += (len(r) + 15) // 16
+
+
+def test_synthetic_move_table_with_many_threshold_conflicts():
+    """Directly synthesised table (random thresholds): ~20 % of rows hold two thresholds, i.e. mode-3 slots whose
+    neighbours are known -- the exact-compare shortcut.  Reads are LF walks with substitutions."""
+    rows, n, cols = PL.synth_move_table(30000, mean_len=8, device="cpu", seed=9)
+    r = np.frombuffer(rows.numpy().tobytes(), dtype=F.ROW_DTYPE)
+    cd = {"ch": r["ch"], "idx": F.u40_unpack(r["idx"]), "interval": r["interval"], "offset": r["offset"], "col_id": r["col_id"],
+          "thr": F.u40_unpack(r["thr"]), "n": n, "bwt_r": len(r)}
+    emu = Emu(cd)
+    assert emu.slow_rows > 1000
+    orc = oracle.Oracle(columns=cd)
+    seqs, off = PL.walk_reads(cols, 400, 150, sub=0.02)
+    p0, c0 = orc.query_batch(seqs, off)
+    assert 0.05 < (p0 == 0).mean() < 0.5
+    for narrow in (False, True):
+        p1, c1 = emu.query(seqs, off, narrow=narrow)
+        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+
+
+@pytest.mark.parametrize("errors", [(0.02, 0.015, 0.015), (0.002, 0.0, 0.0)])
+def test_long_reads_chunk_tasks_with_chain_verification_are_exact(small_index, errors):
+    """Long reads are cut into speculative chunk tasks (warm-up from the initial state) and repaired by fixup_chain;
+    whatever the chunk / warm-up lengths -- including warm-up 0, where almost every chunk must be re-traversed -- the
+    result equals the serial traversal.  Tasks are run in reverse scheduling order to show order independence."""
+    idx = small_index["idx"]
+    sub, ins, dele = errors
+    seqs, off = P.sample_reads(idx["text"], idx["seq_starts"], 30, 3000, sub=sub, ins=ins, dele=dele, seed=6, len_jitter=0.4)
+    rd = [bytes(seqs[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    rd[3] = rd[3][:700] + b"NNNN" + rd[3][704:]          # long irregular reads take the byte path
+    rd[5] = rd[5].lower()
+    rd += adversarial_reads(small_index["haps"])
+    seqs, off = concat_reads(rd)
+    orc = oracle.Oracle(small_index["path"])
+    emu = Emu(small_index["cols"])
+    p0, c0 = orc.query_batch(seqs, off)
+    redone = {}
+    for chunk, warm in ((64, 0), (64, 16), (100, 64), (256, 256), (500, 1000)):
+        for narrow in (False, True):
+            for width in (2, 4):
+                p1, c1 = emu.query_split(seqs, off, chunk, warm, pml_width=width, narrow=narrow)
+                assert np.array_equal(p0, p1) and np.array_equal(c0, c1), (chunk, warm, narrow, width)
+        redone[(chunk, warm)] = emu.redone / max(1, emu.tasks)
+    assert redone[(64, 0)] > 0.9 and redone[(256, 256)] < 0.5 * redone[(64, 16)]

@@ -310,3 +310,45 @@ def test_index_from_primaries_errors_and_cli(cb, golden_dir, tmp_path):
     r = subprocess.run([cli, str(tmp_path / "x.fa")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "x.fa.col_pml").read_bytes() == open(os.path.join(golden_dir, "pan4.col_pml"), "rb").read()
+
+
+def test_synthetic_move_table_from_rows(cb):
+    """configs[4] style: a directly synthesised move table (no text), LF-walk reads; many rows hold two thresholds."""
+    rows, n, cols = PL.synth_move_table(200000, mean_len=12, device="cuda", seed=3)
+    raw = rows.cpu().numpy()
+    seqs, off = PL.walk_reads(cols, 3000, 150, sub=0.02)
+    r = np.frombuffer(raw.tobytes(), dtype=F.ROW_DTYPE)
+    cd = {"ch": r["ch"], "idx": F.u40_unpack(r["idx"]), "interval": r["interval"], "offset": r["offset"], "col_id": r["col_id"],
+          "thr": F.u40_unpack(r["thr"]), "n": n, "bwt_r": len(r)}
+    want_p, want_c = oracle.Oracle(columns=cd).query_batch(seqs, off)
+    tbl = cb.ColPml.from_rows(raw, len(r), n)
+    assert tbl.stats.slow_rows > 10000
+    pml, cid = tbl.query(seqs, off, cb.PML_U8)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("split_env", [{"COLBWT_SPLIT": "1", "COLBWT_SPLIT_CHUNK": "64", "COLBWT_SPLIT_WARM": "16", "COLBWT_SPLIT_MIN": "128"},
+                                       {"COLBWT_SPLIT": "1", "COLBWT_SPLIT_CHUNK": "256", "COLBWT_SPLIT_WARM": "256", "COLBWT_SPLIT_MIN": "512"},
+                                       {"COLBWT_SPLIT": "1"}])
+def test_long_reads_split_into_chunk_tasks(cb, small_index, monkeypatch, split_env):
+    """The long-read path (speculative chunk tasks + k_fixup) on the GPU: tiny chunks with a short warm-up force many
+    re-traversals, the default parameters almost none; both must reproduce the serial result exactly."""
+    for k, v in split_env.items():
+        monkeypatch.setenv(k, v)
+    idx = small_index["idx"]
+    seqs, off = P.sample_reads(idx["text"], idx["seq_starts"], 50, 12000, sub=0.02, ins=0.015, dele=0.015, seed=6, len_jitter=0.5)
+    rd = [bytes(seqs[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    rd[3] = rd[3][:700] + b"NNNN" + rd[3][704:]
+    rd += adversarial_reads(small_index["haps"])
+    s2, o2 = P.sample_reads(idx["text"], idx["seq_starts"], 500, 150, sub=0.01, seed=1)
+    rd += [bytes(s2[int(o2[i]):int(o2[i + 1])]) for i in range(len(o2) - 1)]
+    seqs, off = concat_reads(rd)
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(seqs, off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    b = tbl.batch(seqs, off, cb.PML_U32)
+    assert b.launches == 3          # packed pass, byte pass, chain fix-up
+    b.run(2)
+    p2, c2 = b.download()
+    assert np.array_equal(p2, want_p) and np.array_equal(c2, want_c)
