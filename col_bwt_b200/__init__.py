@@ -111,7 +111,7 @@ class PinnedArray:
         self.array = np.frombuffer((C.c_uint8 * self.nbytes).from_address(self.ptr), dtype=self.dtype, count=n)
 
     def __del__(self):
-        if getattr(self, "ptr", None):
+        if getattr(self, "ptr", None) and _L is not None:
             self.array = None
             _L.colbwt_host_free(self.ptr)
             self.ptr = None
@@ -152,7 +152,7 @@ class Batch:
         return p.value, c.value, n.value
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:   # _L is None during interpreter shutdown
             _L.colbwt_batch_free(self._h)
             self._h = None
 
@@ -239,7 +239,7 @@ class ColPml:
         return Batch(self, seqs, offsets, pml_width, device_slot)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:
             _L.colbwt_index_free(self._h)
             self._h = None
 

@@ -646,6 +646,7 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         bv.cid = k.d_cid;
         bv.n_packed = (uint32_t)st.n_reads;
         bv.n_bytes = (uint32_t)st.n_irregular;
+        if (int rc = upload_plan(st.plan, k.plan, bv, k.stream)) return rc;
         if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[1], k.stream));
         if (int rc = launch_traverse(dt, bv, pml_width, k.d_cursors, k.stream)) return rc;
         if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
