@@ -229,7 +229,21 @@ def time_cpu(ref, kind, seqs, off, threads, target_s):
 
 
 # ------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """The one JSON line goes to the process's original stdout; everything else any library prints to fd 1 (NCCL's
+    version banner, for one) has been redirected to stderr by main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -254,13 +268,12 @@ def main():
         return run_reference(a, have_gpu)
 
     if not have_gpu:
-        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        emit({"error": "no CUDA device: the B200 path has no CPU fallback"})
         return 1
     import torch.distributed as dist
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("COLBWT_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -385,7 +398,7 @@ def main():
         "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind},
         "wall_s_kernel_region": wall_kernel,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0 if (parity and e2e_parity) else 2
@@ -421,7 +434,7 @@ def run_reference(a, have_gpu):
         "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 

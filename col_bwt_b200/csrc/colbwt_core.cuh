@@ -251,6 +251,7 @@ struct BatchView {
     void *pml;              // PmlT[total bases]
     uint8_t *cid;           // [total bases]
     uint32_t n_packed, n_bytes;
+    const uint32_t *n_bytes_dev;   // when set (reads packed on the device), the byte-read count lives here instead of n_bytes
 };
 
 enum LaneState : uint32_t { LANE_IDLE = 0, LANE_LF = 1, LANE_REPOS_SUCC = 2, LANE_REPOS_PRED = 3,

@@ -79,6 +79,9 @@ void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t 
                 uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr);
 
 // kernels (index.cu / traverse.cu) launched through these host wrappers
+// Device-side packing of a chunk's raw bytes (traverse.cu: k_pack_reads).
+int launch_pack(const DeviceTable &dt, const uint8_t *d_bytes, ReadMeta *d_meta, uint32_t n_reads, uint32_t *d_words, ReadMeta *d_meta_b,
+                uint32_t *d_n_irregular, cudaStream_t stream);
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_counters,
                     cudaStream_t stream);
 

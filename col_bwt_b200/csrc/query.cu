@@ -57,6 +57,7 @@ private:
     Pool()
     {
         int n = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) n = std::max(1, n / std::max(1, atoi(e)));   // one process per GPU: share the cores
         if (const char *e = getenv("COLBWT_HOST_THREADS")) n = atoi(e);
         n = std::max(1, std::min(n, 64));
         for (int i = 1; i < n; ++i) workers_.emplace_back([this] { worker(); });
@@ -201,6 +202,43 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
         std::sort(st.meta, st.meta + n_reads, [](const ReadMeta &a, const ReadMeta &b) { return a.len > b.len; });
         st.sorted = true;
     }
+}
+
+// Device-pack variant of prepare_reads: the host only derives the per-read records from the offsets (no sequence
+// byte is read); ReadMeta.out_off doubles as the read's byte offset in the chunk's raw buffer.
+static void prepare_offsets_only(const uint64_t *off, uint64_t r0, uint64_t r1, Staging &st)
+{
+    Pool &pool = Pool::get();
+    const uint64_t n_reads = r1 - r0, base0 = off[r0];
+    st.n_reads = n_reads;
+    st.n_bases = off[r1] - base0;
+    st.n_irregular = st.n_byte_bases = 0;
+    st.plan.clear();
+    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size(), n_reads / 65536 + 1));
+    std::vector<uint64_t> wcount(T + 1, 0);
+    std::vector<uint32_t> tmax(T, 0);
+    pool.parallel_for(T, [&](int t) {
+        uint64_t w = 0;
+        uint32_t mx = 0;
+        for (uint64_t i = r0 + n_reads * t / T; i < r0 + n_reads * (t + 1) / T; ++i) {
+            const uint64_t len = off[i + 1] - off[i];
+            w += words_of(len);
+            mx = std::max<uint32_t>(mx, (uint32_t)len);
+        }
+        wcount[t + 1] = w;
+        tmax[t] = mx;
+    });
+    for (int t = 0; t < T; ++t) wcount[t + 1] += wcount[t];
+    st.n_words = wcount[T];
+    st.max_len = *std::max_element(tmax.begin(), tmax.end());
+    pool.parallel_for(T, [&](int t) {
+        uint64_t w = wcount[t];
+        for (uint64_t i = r0 + n_reads * t / T; i < r0 + n_reads * (t + 1) / T; ++i) {
+            const uint64_t len = off[i + 1] - off[i];
+            st.meta[i - r0] = ReadMeta{off[i] - base0, (uint32_t)len, (uint32_t)w};
+            w += words_of(len);
+        }
+    });
 }
 
 // Device copies of a TaskPlan (grown on demand, reused between chunks / calls).
@@ -573,6 +611,14 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     if (int rc = get_pipeline(idx, chunk_reads, chunk_bases, pml_width, !(is_pinned(pml) && is_pinned(cid)), &plp)) return rc;
     Pipeline &pl = *plp;
     const bool staged_out = !(is_pinned(pml) && is_pinned(cid));
+    // Pack on the device when the input can be DMA-ed as it is (pinned) and no read will be split into chunk tasks:
+    // H2D has headroom (the link is busy in the other direction), host cores often do not (one process per GPU).
+    const SplitParams sp_query = SplitParams::from_env();
+    const char *dp_env = getenv("COLBWT_DEVICE_PACK");
+    // Measured on one B200 with 16 host cores: host packing 19.5 Gbases/s end to end, device packing 17.0 (the extra
+    // 1 B/base of H2D slows the D2H stream on the shared link); so the device packs only when this process has fewer
+    // than 4 packing threads (8 ranks on a 16-core box), or when COLBWT_DEVICE_PACK=1 asks for it.
+    const bool device_pack = (dp_env ? atoi(dp_env) != 0 : Pool::get().size() < 4) && is_pinned(seqs) && max_len < sp_query.min_len;
 
     static const int trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
     struct ChunkTimes { float h2d0, k0, d2h0, end; };
@@ -626,16 +672,22 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         st.meta_b = k.h_meta_b;
         st.words = k.h_words;
         st.bytes = k.h_bytes;
-        prepare_reads(seqs, off, r0, r1, off[n_reads], (uint64_t)dt.sm_count * 1024 / (uint64_t)std::min<int>(SLOTS_PER_DEVICE, 4), st);
+        if (device_pack) prepare_offsets_only(off, r0, r1, st);
+        else prepare_reads(seqs, off, r0, r1, off[n_reads], (uint64_t)dt.sm_count * 1024 / (uint64_t)std::min<int>(SLOTS_PER_DEVICE, 4), st);
         t_pack += now() - t0;
         t0 = now();
 
         if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[0], k.stream));
         CB_CUDA(cudaMemcpyAsync(k.d_meta, k.h_meta, st.n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
-        CB_CUDA(cudaMemcpyAsync(k.d_words, k.h_words, st.n_words * 4, cudaMemcpyHostToDevice, k.stream));
-        if (st.n_irregular) {
-            CB_CUDA(cudaMemcpyAsync(k.d_meta_b, k.h_meta_b, st.n_irregular * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
-            CB_CUDA(cudaMemcpyAsync(k.d_bytes, k.h_bytes, st.n_byte_bases, cudaMemcpyHostToDevice, k.stream));
+        if (device_pack) {
+            CB_CUDA(cudaMemcpyAsync(k.d_bytes, seqs + off[r0], st.n_bases, cudaMemcpyHostToDevice, k.stream));
+            if (int rc = launch_pack(dt, k.d_bytes, k.d_meta, (uint32_t)st.n_reads, k.d_words, k.d_meta_b, (uint32_t *)(k.d_cursors + 3), k.stream)) return rc;
+        } else {
+            CB_CUDA(cudaMemcpyAsync(k.d_words, k.h_words, st.n_words * 4, cudaMemcpyHostToDevice, k.stream));
+            if (st.n_irregular) {
+                CB_CUDA(cudaMemcpyAsync(k.d_meta_b, k.h_meta_b, st.n_irregular * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
+                CB_CUDA(cudaMemcpyAsync(k.d_bytes, k.h_bytes, st.n_byte_bases, cudaMemcpyHostToDevice, k.stream));
+            }
         }
         BatchView bv{};
         bv.meta = k.d_meta;
@@ -646,6 +698,7 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         bv.cid = k.d_cid;
         bv.n_packed = (uint32_t)st.n_reads;
         bv.n_bytes = (uint32_t)st.n_irregular;
+        bv.n_bytes_dev = device_pack ? (const uint32_t *)(k.d_cursors + 3) : nullptr;
         if (int rc = upload_plan(st.plan, k.plan, bv, k.stream)) return rc;
         if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[1], k.stream));
         if (int rc = launch_traverse(dt, bv, pml_width, k.d_cursors, k.stream)) return rc;
@@ -682,9 +735,9 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     }
     if (ev_origin) cudaEventDestroy(ev_origin);
     if (trace)
-        fprintf(stderr, "[colbwt_query] %llu chunks, %.1f Mbases: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, loop %.1f ms, total %.1f ms (%s outputs)\n",
+        fprintf(stderr, "[colbwt_query] %llu chunks, %.1f Mbases: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, loop %.1f ms, total %.1f ms (%s outputs, packing on the %s)\n",
                 (unsigned long long)chunk_no, total_bases / 1e6, t_pack * 1e3, t_drain * 1e3, t_enqueue * 1e3, t_loop * 1e3,
-                (now() - t_begin) * 1e3, staged_out ? "staged" : "pinned");
+                (now() - t_begin) * 1e3, staged_out ? "staged" : "pinned", device_pack ? "device" : "host");
     return COLBWT_OK;
 }
 

@@ -29,7 +29,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const ChunkTask *tasks = PACKED ? bv.tasks : bv.tasks + bv.n_tasks;
     const uint32_t n_tasks = PACKED ? bv.n_tasks : bv.n_tasks_b;       // chunk tasks of split reads go first (longest work)
-    const uint64_t count = (uint64_t)n_tasks + (PACKED ? bv.n_packed : bv.n_bytes);
+    const uint64_t count = (uint64_t)n_tasks + (PACKED ? bv.n_packed : (bv.n_bytes_dev ? __ldg(bv.n_bytes_dev) : bv.n_bytes));
     Lane<PmlT> L;
     bool exhausted = false;
     for (;;) {
@@ -74,6 +74,48 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-side read packing (used by colbwt_query when the caller's sequence buffer is pinned and the reads are short):
+// the raw bytes of a chunk are copied to the device as they are and packed here, so the host touches no sequence
+// byte at all.  Same encoding and same irregular-read rule as pack.cpp.  One warp per read.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_reads(const uint8_t *__restrict__ bytes, ReadMeta *meta, uint32_t n_reads, uint32_t *words,
+                                                     ReadMeta *meta_b, uint32_t *n_irregular)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_reads) return;
+    ReadMeta m = meta[warp];                    // host filled out_off (= byte offset of the read in `bytes`), len, in_off (= word offset)
+    const uint8_t *p = bytes + m.out_off;
+    bool bad = false;
+    for (uint32_t w = lane; w * 16 < m.len; w += 32) {
+        const uint32_t e = min(16u, m.len - w * 16);
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < e; ++k) {
+            const uint8_t c = p[w * 16 + k];
+            bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            v |= (uint32_t)((c >> 1) & 3) << (2 * k);
+        }
+        words[m.in_off + w] = v;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) {
+        const uint32_t k = atomicAdd(n_irregular, 1u);
+        meta_b[k] = ReadMeta{m.out_off, m.len, (uint32_t)m.out_off};   // byte reads index the raw buffer directly
+        meta[warp].len = 0;                                            // skipped by the packed pass
+    }
+}
+
+int launch_pack(const DeviceTable &dt, const uint8_t *d_bytes, ReadMeta *d_meta, uint32_t n_reads, uint32_t *d_words, ReadMeta *d_meta_b,
+                uint32_t *d_n_irregular, cudaStream_t stream)
+{
+    (void)dt;
+    CB_CUDA(cudaMemsetAsync(d_n_irregular, 0, sizeof(uint32_t), stream));
+    if (n_reads) {
+        k_pack_reads<<<(unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, stream>>>(d_bytes, d_meta, n_reads, d_words, d_meta_b, d_n_irregular);
+        CB_CUDA(cudaGetLastError());
+    }
+    return COLBWT_OK;
+}
+
 // One lane per split read: verify its chunk chain, re-traverse the chunks whose speculative start did not converge.
 template <typename PmlT, bool NARROW>
 __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *redone)
@@ -95,7 +137,8 @@ static void launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, cons
                        unsigned long long *cursor, cudaStream_t stream)
 {
     static const int ctas = (getenv("COLBWT_CTAS") && atoi(getenv("COLBWT_CTAS")) == 8) ? 8 : 4;
-    const uint64_t need = ((uint64_t)reads + (PACKED ? bv.n_tasks : bv.n_tasks_b) + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
+    const uint64_t need = (!PACKED && bv.n_bytes_dev) ? (uint64_t)sm_count
+                                                      : ((uint64_t)reads + (PACKED ? bv.n_tasks : bv.n_tasks_b) + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
     const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
     if (ctas == 8) {
@@ -118,7 +161,7 @@ int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, u
         else launch_one<true, uint32_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
         CB_CUDA(cudaGetLastError());
     }
-    if (bv.n_bytes || bv.n_tasks_b) {
+    if (bv.n_bytes || bv.n_tasks_b || bv.n_bytes_dev) {   // with a device-side count the pass is always launched (it exits at once when empty)
         if (pml_width == 2) launch_one<false, uint16_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         else if (pml_width == 1) launch_one<false, uint8_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
         else launch_one<false, uint32_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);

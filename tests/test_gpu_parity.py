@@ -352,3 +352,26 @@ def test_long_reads_split_into_chunk_tasks(cb, small_index, monkeypatch, split_e
     b.run(2)
     p2, c2 = b.download()
     assert np.array_equal(p2, want_p) and np.array_equal(c2, want_c)
+
+
+def test_device_side_packing_with_pinned_input(cb, small_index, monkeypatch):
+    """When the sequence buffer is pinned, raw bytes are copied and packed on the device (k_pack_reads); irregular reads
+    are found there and routed to the byte pass.  Same results as host packing."""
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "50000")
+    rng = np.random.default_rng(4)
+    seqs = small_index["seqs"].copy()
+    off = small_index["off"]
+    for i in rng.choice(len(off) - 1, (len(off) - 1) // 10, replace=False):
+        a, b = int(off[i]), int(off[i + 1])
+        seqs[a + int(rng.integers(0, b - a))] = ord("N") if rng.random() < 0.5 else ord("a")
+    extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
+    seqs = np.concatenate((seqs, extra))
+    off = np.concatenate((off, eoff[1:] + off[-1]))
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"])
+    hs = cb.PinnedArray(seqs.size, np.uint8)
+    hs.array[:] = seqs
+    for env in ("1", "0"):
+        monkeypatch.setenv("COLBWT_DEVICE_PACK", env)
+        pml, cid = tbl.query(hs.array, off, cb.PML_U16)
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c), env
