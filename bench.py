@@ -43,10 +43,14 @@ WORKLOADS = {
     "c2small": dict(H=32, G=1_000_000, snp=9e-4, indel=1e-4, reads=2_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
     "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=400_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
 }
+for _s in (1, 100):   # configs[3]: sub-sample sweep on the 32-haplotype index (tunnel marking; `all` mode is covered by golden fixtures)
+    WORKLOADS[f"c4_s{_s}"] = dict(WORKLOADS["c2"], split_rate=_s)
 WORKLOADS["c5small"] = dict(synthetic_rows=250_000_000, mean_len=16.0, reads=10_000_000, read_len=150, sub=0.01)
 WORKLOADS["tiny"] = dict(H=4, G=50_000, snp=1e-3, indel=0.0, reads=5_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False)
 WORKLOAD_TEXT = {
     "tiny": "4-haplotype x 50 kbp toy (CPU self-test of bench.py only)",
+    "c4_s1": "configs[3]: the configs[1] pangenome marked with tunnels -s 1 (densest chain ids), 10M x 150 bp reads",
+    "c4_s100": "configs[3]: the configs[1] pangenome marked with tunnels -s 100 (sparsest chain ids), 10M x 150 bp reads",
     "c5small": "configs[4] scaled to 2.5e8 directly synthesised move rows (4 GB packed table, DRAM-resident), 10M x 150 bp LF-walk reads, 1% substitutions",
     "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
@@ -124,7 +128,7 @@ def build_workload(name: str, device: str, verbose: bool):
     if not os.path.exists(meta_path):
         t0 = time.time()
         haps = P.make_haplotypes(w["G"], w["H"], snp=w["snp"], indel=w["indel"], seed=1, tree=w["tree"])
-        idx = PL.build_index(haps, with_revcomp=True, split_rate=10, min_mum=20, device=device, verbose=verbose)
+        idx = PL.build_index(haps, with_revcomp=True, split_rate=w.get("split_rate", 10), min_mum=20, device=device, verbose=verbose)
         PL.write_col_pml(stem + ".col_pml", idx["columns"])
         np.save(stem + ".text.npy", idx["text"])
         np.save(stem + ".seq_starts.npy", idx["seq_starts"])
@@ -328,6 +332,17 @@ def main():
     ref, kind = cpu_reference(path)
     want = ref.query_batch(seqs[: int(off[k])], off[: k + 1])
     parity = bool(np.array_equal(pml_d[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(cid_d[: int(off[k])], want[1]))
+    # size-independent invariants on a large slice of the measured output: PML[j] is 0 or PML[j+1]+1
+    # inside a read, and never exceeds the bases left of the read
+    kk = min(n_reads, 500_000)
+    sl = pml_d[: int(off[kk])].astype(np.int64)
+    nxt = np.empty_like(sl)
+    nxt[:-1] = sl[1:]
+    ends = off[1: kk + 1].astype(np.int64) - 1
+    nxt[ends] = 0
+    left = np.repeat(off[1: kk + 1].astype(np.int64), np.diff(off[: kk + 1]).astype(np.int64)) - np.arange(sl.size)
+    properties = bool((((sl == 0) | (sl == nxt + 1)) & (sl <= left)).all())
+    del sl, nxt, left
     mismatch_frac = float((pml_d[: min(n_bases, 50_000_000)] == 0).mean())
     cid_frac = float((cid_d[: min(n_bases, 50_000_000)] > 0).mean())
     del pml_d, cid_d
@@ -395,13 +410,14 @@ def main():
                 "pml_bytes": width, "api": "colbwt_query (host pinned buffers; host 2-bit packing inside the timed region)"},
         "gpu_launches": batch.launches * a.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-        "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind},
+        "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind,
+                             "pml_invariants_on_first_reads": {"reads": kk, "ok": properties}},
         "wall_s_kernel_region": wall_kernel,
     }
     emit(out)
     if world > 1:
         dist.destroy_process_group()
-    return 0 if (parity and e2e_parity) else 2
+    return 0 if (parity and e2e_parity and properties) else 2
 
 
 def run_reference(a, have_gpu):

@@ -12,12 +12,13 @@ SO = os.path.join(HERE, "native", "libemulate.so")
 SRC = [os.path.join(HERE, "native", "emulate.cpp"), os.path.join(HERE, "..", "col_bwt_b200", "csrc", "pack.cpp")]
 HDR = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "colbwt_core.cuh")
 HDR2 = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "tasks.h")
+HDR3 = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "fastx.h")
 
 
 def build():
-    newest = max(os.path.getmtime(p) for p in SRC + [HDR, HDR2])
+    newest = max(os.path.getmtime(p) for p in SRC + [HDR, HDR2, HDR3])
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRC, check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRC + ["-lz"], check=True)
 
 
 class Emu:

@@ -10,6 +10,7 @@
 
 #include "../../col_bwt_b200/csrc/colbwt_core.cuh"
 #include "../../col_bwt_b200/csrc/tasks.h"
+#include "../../col_bwt_b200/csrc/fastx.h"
 
 namespace colbwt {
 bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
@@ -160,6 +161,36 @@ uint64_t emu_query_split(EmuTable *t, const uint8_t *seqs, const uint64_t *off, 
     if (pml_width == 1) return narrow ? emu_split_impl<uint8_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint8_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
     if (pml_width == 2) return narrow ? emu_split_impl<uint16_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint16_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
     return narrow ? emu_split_impl<uint32_t, true>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out) : emu_split_impl<uint32_t, false>(t, seqs, off, n_reads, pml, cid, sp, n_tasks_out);
+}
+
+// The CLI's FASTA/FASTQ(.gz) reader (fastx.h): parses `path` in batches of at most max_bases / max_reads and returns the
+// total number of records; sequences are concatenated into seq_out, offsets[n+1], ids joined by '\n' into ids_out.
+uint64_t emu_fastx(const char *path, uint64_t max_bases, uint64_t max_reads, uint8_t *seq_out, uint64_t seq_cap, uint64_t *off_out,
+                   uint64_t off_cap, char *ids_out, uint64_t ids_cap, uint64_t *n_batches)
+{
+    FastxReader rd(path);
+    if (!rd.ok()) return UINT64_MAX;
+    std::vector<uint8_t> seqs;
+    std::vector<uint64_t> off;
+    std::vector<std::string> ids;
+    uint64_t n = 0, bases = 0, idp = 0, batches = 0;
+    off_out[0] = 0;
+    while (rd.next_batch(seqs, off, ids, max_bases, max_reads)) {
+        ++batches;
+        for (size_t i = 0; i < ids.size(); ++i) {
+            const uint64_t len = off[i + 1] - off[i];
+            if (bases + len > seq_cap || n + 2 > off_cap || idp + ids[i].size() + 1 > ids_cap) return UINT64_MAX - 1;
+            memcpy(seq_out + bases, seqs.data() + off[i], len);
+            bases += len;
+            off_out[++n] = bases;
+            memcpy(ids_out + idp, ids[i].data(), ids[i].size());
+            idp += ids[i].size();
+            ids_out[idp++] = '\n';
+        }
+    }
+    ids_out[idp] = 0;
+    *n_batches = batches;
+    return n;
 }
 
 int emu_pack(const uint8_t *seq, uint64_t len, uint32_t *words) { return pack_read_2bit(seq, len, words) ? 1 : 0; }
