@@ -334,13 +334,13 @@ def main():
     parity = bool(np.array_equal(pml_d[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(cid_d[: int(off[k])], want[1]))
     # size-independent invariants on a large slice of the measured output: PML[j] is 0 or PML[j+1]+1
     # inside a read, and never exceeds the bases left of the read
-    kk = min(n_reads, 500_000)
-    sl = pml_d[: int(off[kk])].astype(np.int64)
+    n_inv = min(n_reads, 500_000)
+    sl = pml_d[: int(off[n_inv])].astype(np.int64)
     nxt = np.empty_like(sl)
     nxt[:-1] = sl[1:]
-    ends = off[1: kk + 1].astype(np.int64) - 1
+    ends = off[1: n_inv + 1].astype(np.int64) - 1
     nxt[ends] = 0
-    left = np.repeat(off[1: kk + 1].astype(np.int64), np.diff(off[: kk + 1]).astype(np.int64)) - np.arange(sl.size)
+    left = np.repeat(off[1: n_inv + 1].astype(np.int64), np.diff(off[: n_inv + 1]).astype(np.int64)) - np.arange(sl.size)
     properties = bool((((sl == 0) | (sl == nxt + 1)) & (sl <= left)).all())
     del sl, nxt, left
     mismatch_frac = float((pml_d[: min(n_bases, 50_000_000)] == 0).mean())
@@ -411,7 +411,7 @@ def main():
         "gpu_launches": batch.launches * a.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind,
-                             "pml_invariants_on_first_reads": {"reads": kk, "ok": properties}},
+                             "pml_invariants_on_first_reads": {"reads": n_inv, "ok": properties}},
         "wall_s_kernel_region": wall_kernel,
     }
     emit(out)
