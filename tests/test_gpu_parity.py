@@ -375,3 +375,44 @@ def test_device_side_packing_with_pinned_input(cb, small_index, monkeypatch):
         monkeypatch.setenv("COLBWT_DEVICE_PACK", env)
         pml, cid = tbl.query(hs.array, off, cb.PML_U16)
         assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c), env
+
+
+def test_degenerate_batches_and_offset_base(cb, small_index):
+    """Empty batch, all-empty reads, a batch whose offsets do not start at 0, repeated calls on one handle."""
+    tbl = cb.ColPml.load(small_index["path"])
+    pml, cid = tbl.query(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert pml.size == 0 and cid.size == 0
+    pml, cid = tbl.query(np.zeros(0, np.uint8), np.zeros(6, np.uint64))          # five empty reads
+    assert pml.size == 0 and cid.size == 0
+    seqs, off = small_index["seqs"], small_index["off"]
+    orc = oracle.Oracle(small_index["path"])
+    # offsets starting at read 100 of the same buffer: outputs are relative to off[0]
+    sub_off = off[100:301].copy()
+    want_p, want_c = orc.query_batch(seqs[int(sub_off[0]):int(sub_off[-1])], sub_off - sub_off[0])
+    pml, cid = tbl.query(seqs, sub_off)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    b = tbl.batch(seqs, sub_off)
+    b.run(1)
+    p2, c2 = b.download()
+    assert np.array_equal(p2.astype(np.uint32), want_p) and np.array_equal(c2, want_c)
+    # a batch that is one base long
+    pml, cid = tbl.query(np.frombuffer(b"G", np.uint8), np.array([0, 1], np.uint64), cb.PML_U8)
+    w = orc.query(b"G")
+    assert pml.tolist() == w[0].tolist() and cid.tolist() == w[1].tolist()
+
+
+def test_two_threads_share_one_index(cb, small_index):
+    import threading
+    tbl = cb.ColPml.load(small_index["path"])
+    seqs, off = small_index["seqs"], small_index["off"]
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    results = [None, None]
+
+    def work(i):
+        for _ in range(3):
+            results[i] = tbl.query(seqs, off)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for pml, cid in results:
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
