@@ -273,69 +273,76 @@ template <typename PmlT> struct Lane {
     uint32_t slot = NO_SLOT;
     uint32_t rw = 0;        // current packed word
     uint64_t out_base = 0;
-    uint32_t cnt = 0;       // staged outputs
-    uint32_t accp[4] = {0, 0, 0, 0};   // 8 staged u16 (or u8) PML values, lowest position in the low bits
-    uint32_t accc[2] = {0, 0};         // 8 staged CID bytes
+    uint32_t hi_slot = 64;  // highest valid slot of the output block being staged (64 = nothing staged yet)
 };
 
-template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const BatchView &bv, uint64_t g)
+// ---------------------------------------------------------------------------------------------------------
+// Output staging.  Scattered 8/16-byte stores from ~150 k lanes cost 20 % of the random-gather rate (each becomes its
+// own partial DRAM write: profiles/r1/l2stream*.log), 64-byte bursts per lane do not.  Every lane therefore stages one
+// aligned block of 64 output positions -- 64 CID bytes and 64 PML values -- in shared memory and writes it out as
+// consecutive 16-byte vectors when the block is complete (or the read ends).  Words are interleaved across the
+// threads of the CTA (word w of thread t at [w * stride + t]), so a warp's accesses never conflict on a bank.
+// ---------------------------------------------------------------------------------------------------------
+struct Stage {
+    uint32_t *base;     // this thread's word 0
+    uint32_t stride;    // words between consecutive words of one thread (CTA size on the device, 1 on the host)
+};
+constexpr uint32_t STAGE_BLOCK = 64;
+constexpr uint32_t STAGE_CID_WORDS = STAGE_BLOCK / 4;
+template <typename PmlT> constexpr uint32_t stage_words() { return STAGE_CID_WORDS + (sizeof(PmlT) < 4 ? STAGE_BLOCK * (uint32_t)sizeof(PmlT) / 4 : 0); }
+
+CB_HD uint32_t &stage_word(const Stage &sg, uint32_t w) { return sg.base[w * sg.stride]; }
+
+// Write slots [lo, hi] of one staged array (element size ES bytes, first word w0) to dst (= address of slot 0).
+template <int ES> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *dst, uint32_t lo, uint32_t hi)
 {
-    uint8_t *cid = bv.cid + g;
-    if (L.cnt == 8) {   // aligned full group: g % 8 == 0
+    constexpr uint32_t PER_VEC = 16 / ES;                       // slots per 16-byte vector
+#pragma unroll
+    for (uint32_t q = 0; q < STAGE_BLOCK / PER_VEC; ++q) {
+        const uint32_t s0 = q * PER_VEC, s1 = s0 + PER_VEC - 1;
+        if (s1 < lo || s0 > hi) continue;
+        const uint32_t w = w0 + q * 4;
+        if (s0 >= lo && s1 <= hi) {
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-        st_v2(cid, L.accc[0], L.accc[1]);
-        if (sizeof(PmlT) == 2)
-            st_v4(reinterpret_cast<uint16_t *>(bv.pml) + g, L.accp[0], L.accp[1], L.accp[2], L.accp[3]);
-        else if (sizeof(PmlT) == 1)
-            st_v2(reinterpret_cast<uint8_t *>(bv.pml) + g, L.accp[0], L.accp[1]);
+            st_v4(dst + s0 * ES, stage_word(sg, w), stage_word(sg, w + 1), stage_word(sg, w + 2), stage_word(sg, w + 3));
 #else
-        for (int t = 0; t < 8; ++t) cid[t] = (uint8_t)(L.accc[t >> 2] >> (8 * (t & 3)));
-        if (sizeof(PmlT) == 2)
-            for (int t = 0; t < 8; ++t) reinterpret_cast<uint16_t *>(bv.pml)[g + t] = (uint16_t)(L.accp[t >> 1] >> (16 * (t & 1)));
-        else if (sizeof(PmlT) == 1)
-            for (int t = 0; t < 8; ++t) reinterpret_cast<uint8_t *>(bv.pml)[g + t] = (uint8_t)(L.accp[t >> 2] >> (8 * (t & 3)));
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t v = stage_word(sg, w + k);
+                for (uint32_t b = 0; b < 4; ++b) dst[s0 * ES + 4 * k + b] = (uint8_t)(v >> (8 * b));
+            }
 #endif
-    } else {
-        uint32_t c0 = L.accc[0], c1 = L.accc[1];
-        uint32_t p0 = L.accp[0], p1 = L.accp[1], p2 = L.accp[2], p3 = L.accp[3];
-        for (uint32_t t = 0; t < L.cnt; ++t) {
-            cid[t] = (uint8_t)c0;
-            c0 = (c0 >> 8) | (c1 << 24);
-            c1 >>= 8;
-            if (sizeof(PmlT) == 2) {
-                reinterpret_cast<uint16_t *>(bv.pml)[g + t] = (uint16_t)p0;
-                p0 = (p0 >> 16) | (p1 << 16);
-                p1 = (p1 >> 16) | (p2 << 16);
-                p2 = (p2 >> 16) | (p3 << 16);
-                p3 >>= 16;
-            } else if (sizeof(PmlT) == 1) {
-                reinterpret_cast<uint8_t *>(bv.pml)[g + t] = (uint8_t)p0;
-                p0 = (p0 >> 8) | (p1 << 24);
-                p1 >>= 8;
+        } else {                                                // ragged edge of a read: element by element
+            const uint32_t a = s0 > lo ? s0 : lo, e = s1 < hi ? s1 : hi;
+            for (uint32_t sl = a; sl <= e; ++sl) {
+                const uint32_t v = stage_word(sg, w0 + sl * ES / 4) >> (8 * ((sl * ES) & 3));
+                if (ES == 1) dst[sl] = (uint8_t)v;
+                else reinterpret_cast<uint16_t *>(dst)[sl] = (uint16_t)v;
             }
         }
     }
-    L.cnt = 0;
 }
 
-template <typename PmlT> CB_HD void lane_emit(Lane<PmlT> &L, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)   // jj < emit_top
+template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const Stage &sg, const BatchView &bv, uint64_t g)
+{
+    const uint32_t lo = (uint32_t)(g & (STAGE_BLOCK - 1));
+    const uint64_t blk = g - lo;
+    stage_write<1>(sg, 0, bv.cid + blk, lo, L.hi_slot);
+    if (sizeof(PmlT) == 1) stage_write<1>(sg, STAGE_CID_WORDS, reinterpret_cast<uint8_t *>(bv.pml) + blk, lo, L.hi_slot);
+    else if (sizeof(PmlT) == 2) stage_write<2>(sg, STAGE_CID_WORDS, reinterpret_cast<uint8_t *>(bv.pml) + 2 * blk, lo, L.hi_slot);
+    L.hi_slot = STAGE_BLOCK - 1;                                // the next block below starts full-width
+}
+
+template <typename PmlT>
+CB_HD void lane_emit(Lane<PmlT> &L, const Stage &sg, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)   // jj < emit_top
 {
     const uint64_t g = L.out_base + jj;
-    L.accc[1] = (L.accc[1] << 8) | (L.accc[0] >> 24);
-    L.accc[0] = (L.accc[0] << 8) | cid;
-    if (sizeof(PmlT) == 2) {
-        L.accp[3] = (L.accp[3] << 16) | (L.accp[2] >> 16);
-        L.accp[2] = (L.accp[2] << 16) | (L.accp[1] >> 16);
-        L.accp[1] = (L.accp[1] << 16) | (L.accp[0] >> 16);
-        L.accp[0] = (L.accp[0] << 16) | (plen & 0xFFFFu);
-    } else if (sizeof(PmlT) == 1) {
-        L.accp[1] = (L.accp[1] << 8) | (L.accp[0] >> 24);
-        L.accp[0] = (L.accp[0] << 8) | (plen & 0xFFu);
-    } else {
-        reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
-    }
-    ++L.cnt;
-    if ((g & 7) == 0 || jj == L.j_stop) lane_flush(L, bv, g);
+    const uint32_t slot = (uint32_t)(g & (STAGE_BLOCK - 1));
+    if (L.hi_slot >= STAGE_BLOCK) L.hi_slot = slot;             // first output of this read / chunk
+    reinterpret_cast<uint8_t *>(&stage_word(sg, slot >> 2))[slot & 3] = (uint8_t)cid;
+    if (sizeof(PmlT) == 1) reinterpret_cast<uint8_t *>(&stage_word(sg, STAGE_CID_WORDS + (slot >> 2)))[slot & 3] = (uint8_t)plen;
+    else if (sizeof(PmlT) == 2) reinterpret_cast<uint16_t *>(&stage_word(sg, STAGE_CID_WORDS + (slot >> 1)))[slot & 1] = (uint16_t)plen;
+    else reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
+    if (slot == 0 || jj == L.j_stop) lane_flush(L, sg, bv, g);
 }
 
 // Start read `m` on this lane (zero-length reads are skipped by the caller).
@@ -351,7 +358,7 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const
     L.slot = NO_SLOT;
     L.in_off = m.in_off;
     L.out_base = m.out_off;
-    L.cnt = 0;
+    L.hi_slot = STAGE_BLOCK;
     if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
 }
 
@@ -368,7 +375,7 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin_task(Lane<PmlT> &L, 
     L.slot = k.slot;
     L.in_off = k.in_off;
     L.out_base = k.out_off;
-    L.cnt = 0;
+    L.hi_slot = STAGE_BLOCK;
     if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.top - 1) >> 4));
 }
 
@@ -386,13 +393,13 @@ CB_HD void lane_begin_from_state(Lane<PmlT> &L, const BatchView &bv, const Chunk
     L.slot = k.slot;
     L.in_off = k.in_off;
     L.out_base = k.out_off;
-    L.cnt = 0;
+    L.hi_slot = STAGE_BLOCK;
     if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.hi - 1) >> 4));
 }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
 template <bool PACKED, typename PmlT>
-CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
+CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
 {
     const uint32_t len = row_len(row);
     if (L.state != LANE_LF) {
@@ -438,7 +445,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
     } else {
         L.plen = 0;                              // col_bwt.hpp:520-523
     }
-    if (jj < L.emit_top) lane_emit(L, bv, jj, L.plen, cid);
+    if (jj < L.emit_top) lane_emit(L, sg, bv, jj, L.plen, cid);
     if (jj == L.j_stop && L.slot == NO_SLOT) {   // whole read: the reference's last LF step has no observable effect
         L.state = LANE_IDLE;
         return;
@@ -484,7 +491,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const TableView &t, const BatchView &bv, con
 
 // Narrow-layout twin of lane_step.  `w` = hot[addr], or cold[addr] when the lane is in LANE_COLD.
 template <bool PACKED, typename PmlT>
-CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut)
+CB_HD void lane_step_narrow(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut)
 {
     const uint32_t st = L.state & 7u;
     if (st == LANE_COLD) {
@@ -557,7 +564,7 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
     if (!PACKED && code >= CODE_OTHER)
         match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
     L.plen = match ? L.plen + 1 : 0;
-    if (jj < L.emit_top) lane_emit(L, bv, jj, L.plen, cid);
+    if (jj < L.emit_top) lane_emit(L, sg, bv, jj, L.plen, cid);
     if (jj == L.j_stop && L.slot == NO_SLOT) {
         L.state = LANE_IDLE;
         return;
@@ -584,14 +591,14 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const TableView &t, const BatchView &
 
 // Run a lane to completion on its own (fixup re-traversal on the device, every lane in the host emulation).
 template <bool PACKED, bool NARROW, typename PmlT>
-CB_HD void lane_run(Lane<PmlT> &L, const TableView &t, const BatchView &bv, const uint8_t *code_lut)
+CB_HD void lane_run(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, const uint8_t *code_lut)
 {
     while (L.state != LANE_IDLE) {
         if (NARROW) {
             const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
-            lane_step_narrow<PACKED>(L, t, bv, ld_row64(base + L.addr), code_lut);
+            lane_step_narrow<PACKED>(L, sg, t, bv, ld_row64(base + L.addr), code_lut);
         } else {
-            lane_step<PACKED>(L, t, bv, ld_row(t.rows + L.addr), code_lut);
+            lane_step<PACKED>(L, sg, t, bv, ld_row(t.rows + L.addr), code_lut);
         }
     }
 }
@@ -599,7 +606,7 @@ CB_HD void lane_run(Lane<PmlT> &L, const TableView &t, const BatchView &bv, cons
 // Verify / repair the chunk chain of one split read, top chunk first (see ChunkTask).  Returns the number of chunks
 // that had to be re-traversed.
 template <bool PACKED, bool NARROW, typename PmlT>
-CB_HD uint32_t fixup_chain(const TableView &t, const BatchView &bv, const ChainDesc &c, const uint8_t *code_lut)
+CB_HD uint32_t fixup_chain(const Stage &sg, const TableView &t, const BatchView &bv, const ChainDesc &c, const uint8_t *code_lut)
 {
     uint32_t redone = 0;
     PmlT *pml = reinterpret_cast<PmlT *>(bv.pml);
@@ -623,7 +630,7 @@ CB_HD uint32_t fixup_chain(const TableView &t, const BatchView &bv, const ChainD
         } else {
             Lane<PmlT> L;
             lane_begin_from_state<PACKED>(L, bv, k, truth);
-            lane_run<PACKED, NARROW>(L, t, bv, code_lut);
+            lane_run<PACKED, NARROW>(L, sg, t, bv, code_lut);
             ++redone;
         }
     }

@@ -21,10 +21,12 @@ __global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
     __shared__ uint8_t code_lut[256];
+    extern __shared__ uint32_t stage_mem[];                     // stage_words<PmlT>() words per thread, thread-interleaved
     if (!PACKED) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) code_lut[i] = code_lut_g[i];
         __syncthreads();
     }
+    const Stage sg{stage_mem + threadIdx.x, TRAVERSE_THREADS};
     const uint32_t lane = threadIdx.x & 31;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const ChunkTask *tasks = PACKED ? bv.tasks : bv.tasks + bv.n_tasks;
@@ -65,10 +67,10 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
             if (NARROW) {
                 const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
                 const uint64_t w = ld_row64(base + L.addr);
-                lane_step_narrow<PACKED>(L, t, bv, w, code_lut);
+                lane_step_narrow<PACKED>(L, sg, t, bv, w, code_lut);
             } else {
                 const Row row = ld_row(t.rows + L.addr);
-                lane_step<PACKED>(L, t, bv, row, code_lut);
+                lane_step<PACKED>(L, sg, t, bv, row, code_lut);
             }
         }
     }
@@ -121,33 +123,39 @@ template <typename PmlT, bool NARROW>
 __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *redone)
 {
     __shared__ uint8_t code_lut[256];
+    __shared__ uint32_t stage_mem[128 * stage_words<PmlT>()];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) code_lut[i] = code_lut_g[i];
     __syncthreads();
+    const Stage sg{stage_mem + threadIdx.x, 128};
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= bv.n_chains) return;
     const ChainDesc d = bv.chains[c];
-    const uint32_t n = d.packed ? fixup_chain<true, NARROW, PmlT>(t, bv, d, code_lut) : fixup_chain<false, NARROW, PmlT>(t, bv, d, code_lut);
+    const uint32_t n = d.packed ? fixup_chain<true, NARROW, PmlT>(sg, t, bv, d, code_lut) : fixup_chain<false, NARROW, PmlT>(sg, t, bv, d, code_lut);
     if (n) atomicAdd(redone, (unsigned long long)n);
 }
 
-// CTAs per SM: 4 (1024 lanes per SM, 48 registers, no spills) is the measured optimum on DRAM-resident tables -- more
-// lanes in flight only thrash the L2 (profiles/r1/variant_sweep2.log); COLBWT_CTAS=8 selects the full-occupancy build.
+// 4 CTAs of 256 lanes per SM (48-56 registers, no spills): the measured optimum on DRAM-resident tables -- more lanes in
+// flight only thrash the L2 (profiles/r1/variant_sweep2.log) -- and what the output staging (up to 48 KB per CTA) allows.
+constexpr int TRAVERSE_CTAS = 4;
 template <bool PACKED, typename PmlT>
-static void launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut,
-                       unsigned long long *cursor, cudaStream_t stream)
+static int launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut,
+                      unsigned long long *cursor, cudaStream_t stream)
 {
-    static const int ctas = (getenv("COLBWT_CTAS") && atoi(getenv("COLBWT_CTAS")) == 8) ? 8 : 4;
     const uint64_t need = (!PACKED && bv.n_bytes_dev) ? (uint64_t)sm_count
                                                       : ((uint64_t)reads + (PACKED ? bv.n_tasks : bv.n_tasks_b) + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * ctas));
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * TRAVERSE_CTAS));
+    const size_t smem = (size_t)TRAVERSE_THREADS * stage_words<PmlT>() * sizeof(uint32_t);
     const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
-    if (ctas == 8) {
-        if (narrow) k_traverse<PACKED, PmlT, 8, true><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
-        else k_traverse<PACKED, PmlT, 8, false><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
+    if (narrow) {
+        auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, true>;
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TRAVERSE_THREADS, smem, stream>>>(dt.view, bv, lut, cursor);
     } else {
-        if (narrow) k_traverse<PACKED, PmlT, 4, true><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
-        else k_traverse<PACKED, PmlT, 4, false><<<grid, TRAVERSE_THREADS, 0, stream>>>(dt.view, bv, lut, cursor);
+        auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, false>;
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TRAVERSE_THREADS, smem, stream>>>(dt.view, bv, lut, cursor);
     }
+    return COLBWT_OK;
 }
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)
@@ -155,16 +163,19 @@ int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, u
     // [0] cursor of the packed work list, [1] of the byte work list, [2] chunks re-traversed by k_fixup
     CB_CUDA(cudaMemsetAsync(d_cursors, 0, 3 * sizeof(unsigned long long), stream));
     const uint8_t *lut = (const uint8_t *)dt.d_code_lut;
+    int rc = COLBWT_OK;
     if (bv.n_packed || bv.n_tasks) {
-        if (pml_width == 2) launch_one<true, uint16_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
-        else if (pml_width == 1) launch_one<true, uint8_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
-        else launch_one<true, uint32_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        if (pml_width == 2) rc = launch_one<true, uint16_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else if (pml_width == 1) rc = launch_one<true, uint8_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        else rc = launch_one<true, uint32_t>(dt.sm_count, bv.n_packed, dt, bv, lut, d_cursors, stream);
+        if (rc) return rc;
         CB_CUDA(cudaGetLastError());
     }
     if (bv.n_bytes || bv.n_tasks_b || bv.n_bytes_dev) {   // with a device-side count the pass is always launched (it exits at once when empty)
-        if (pml_width == 2) launch_one<false, uint16_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
-        else if (pml_width == 1) launch_one<false, uint8_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
-        else launch_one<false, uint32_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        if (pml_width == 2) rc = launch_one<false, uint16_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else if (pml_width == 1) rc = launch_one<false, uint8_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        else rc = launch_one<false, uint32_t>(dt.sm_count, bv.n_bytes, dt, bv, lut, d_cursors + 1, stream);
+        if (rc) return rc;
         CB_CUDA(cudaGetLastError());
     }
     if (bv.n_chains) {   // split reads exist: verify / repair their chunk chains (d_cursors[2] counts re-traversed chunks)

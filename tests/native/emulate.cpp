@@ -43,6 +43,8 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
     bv.pml = pml;
     bv.cid = cid;
     bv.bytes = seqs;
+    uint32_t stage_buf[64] = {0};
+    const Stage sg{stage_buf, 1};
     std::vector<uint32_t> words;
     std::vector<uint64_t> word_off(n_reads, 0);
     std::vector<char> is_packed(n_reads, 0);
@@ -71,10 +73,10 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
         Lane<PmlT> L;
         if (k < plan.n_tasks) {
             lane_begin_task<true>(L, t->view, bv, plan.tasks[k]);
-            lane_run<true, NARROW>(L, t->view, bv, t->code_lut);
+            lane_run<true, NARROW>(L, sg, t->view, bv, t->code_lut);
         } else {
             lane_begin_task<false>(L, t->view, bv, plan.tasks[k]);
-            lane_run<false, NARROW>(L, t->view, bv, t->code_lut);
+            lane_run<false, NARROW>(L, sg, t->view, bv, t->code_lut);
         }
     }
     for (uint64_t i = 0; i < n_reads; ++i) {   // whole reads
@@ -82,12 +84,12 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
         if (!len || len >= sp.min_len) continue;
         Lane<PmlT> L;
         ReadMeta m{off[i], (uint32_t)len, is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i]};
-        if (is_packed[i]) { lane_begin<true>(L, t->view, bv, m); lane_run<true, NARROW>(L, t->view, bv, t->code_lut); }
-        else { lane_begin<false>(L, t->view, bv, m); lane_run<false, NARROW>(L, t->view, bv, t->code_lut); }
+        if (is_packed[i]) { lane_begin<true>(L, t->view, bv, m); lane_run<true, NARROW>(L, sg, t->view, bv, t->code_lut); }
+        else { lane_begin<false>(L, t->view, bv, m); lane_run<false, NARROW>(L, sg, t->view, bv, t->code_lut); }
     }
     uint64_t redone = 0;
     for (const ChainDesc &c : plan.chains)
-        redone += c.packed ? fixup_chain<true, NARROW, PmlT>(t->view, bv, c, t->code_lut) : fixup_chain<false, NARROW, PmlT>(t->view, bv, c, t->code_lut);
+        redone += c.packed ? fixup_chain<true, NARROW, PmlT>(sg, t->view, bv, c, t->code_lut) : fixup_chain<false, NARROW, PmlT>(sg, t->view, bv, c, t->code_lut);
     *n_tasks_out = plan.tasks.size();
     return redone;
 }
@@ -215,6 +217,8 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
     const bool narrow = (force_bytes & 2) != 0;
     force_bytes &= 1;
     uint64_t iters = 0;
+    uint32_t stage_buf[64] = {0};
+    const Stage sg{stage_buf, 1};
     BatchView bv{};
     bv.pml = pml;
     bv.cid = cid;
@@ -233,10 +237,10 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
             while (L.state != LANE_IDLE) {
                 if (narrow) {
                     const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t->view.cold : t->view.hot;
-                    lane_step_narrow<P>(L, t->view, bv, base[L.addr], t->code_lut);
+                    lane_step_narrow<P>(L, sg, t->view, bv, base[L.addr], t->code_lut);
                 } else {
                     if (g_trace_on) g_trace.push_back(L.addr);
-                    lane_step<P>(L, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                    lane_step<P>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
                 }
                 ++iters;
             }
