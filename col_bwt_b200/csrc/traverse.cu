@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchVie
 }
 
 // 4 CTAs of 256 lanes per SM (48-56 registers, no spills): the measured optimum on DRAM-resident tables -- more lanes in
-// flight only thrash the L2 (profiles/r1/variant_sweep2.log) -- and what the output staging (up to 48 KB per CTA) allows.
+// flight only thrash the L2 (profiles/r1/variant_sweep2.log; re-measured with the output staging: 3/4/5/6 CTAs = 40.9 /
+// 44.8 / 39.3 / 23.1 Gbases/s on C2) -- and what the output staging (up to 48 KB per CTA) allows.
 constexpr int TRAVERSE_CTAS = 4;
 template <bool PACKED, typename PmlT>
 static int launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut,

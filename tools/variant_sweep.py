@@ -9,7 +9,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     path, text, ss, meta = bench.build_workload(wl, "cuda:0", False)
     seqs, off = bench.make_reads(wl, text, ss, 0, int(sys.argv[3]) if len(sys.argv) > 3 else None, "cuda:0")
     tbl = cb.ColPml.load(path)
-    b = tbl.batch(seqs, off)
+    b = tbl.batch(seqs, off, int(os.environ.get('PMLW', '2')))
     for _ in range(3): b.run(1)
     ms = b.run(5)
     print(json.dumps({"narrow": os.environ.get("COLBWT_NARROW", ""), "ctas": os.environ.get("COLBWT_CTAS", ""), "ms": ms, "gbases_s": seqs.size / ms / 1e6}))
