@@ -297,6 +297,14 @@ CB_HD uint32_t &stage_word(const Stage &sg, uint32_t w) { return sg.base[w * sg.
 template <int ES> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *dst, uint32_t lo, uint32_t hi)
 {
     constexpr uint32_t PER_VEC = 16 / ES;                       // slots per 16-byte vector
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+    if (lo == 0 && hi == STAGE_BLOCK - 1) {                     // complete block: one straight burst
+#pragma unroll
+        for (uint32_t q = 0; q < STAGE_BLOCK / PER_VEC; ++q)
+            st_v4(dst + q * 16, stage_word(sg, w0 + 4 * q), stage_word(sg, w0 + 4 * q + 1), stage_word(sg, w0 + 4 * q + 2), stage_word(sg, w0 + 4 * q + 3));
+        return;
+    }
+#endif
 #pragma unroll
     for (uint32_t q = 0; q < STAGE_BLOCK / PER_VEC; ++q) {
         const uint32_t s0 = q * PER_VEC, s1 = s0 + PER_VEC - 1;
