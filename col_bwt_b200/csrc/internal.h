@@ -70,18 +70,19 @@ int build_device_table_from_primaries(DeviceTable &dt, int device, const Primari
 int export_rows(const DeviceTable &dt, uint64_t first, uint64_t count, void *host_out);
 
 // pack.cpp: host-side 2-bit packer.
-// Packs reads [r0, r1) of a batch: 2-bit words at word offsets word_off[i] (relative to words),
-// returns false for reads that contain a byte outside ACGT (their words are garbage, caller ships bytes).
+// One read: returns false if it contains a byte outside ACGT (its words are then garbage, the caller ships bytes).
 bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
 // Packs reads [r0, r1) of a batch (one thread's slice): metas at meta[i - r_base], words from word index w on;
 // seq_end = number of readable bytes in seqs (bounds the 32-byte over-reads); irregular read numbers go to irr.
 void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t r_base, uint64_t base0,
                 uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr);
 
-// kernels (index.cu / traverse.cu) launched through these host wrappers
+// Kernels launched through host wrappers (traverse.cu).
 // Device-side packing of a chunk's raw bytes (traverse.cu: k_pack_reads).
 int launch_pack(const DeviceTable &dt, const uint8_t *d_bytes, ReadMeta *d_meta, uint32_t n_reads, uint32_t *d_words, ReadMeta *d_meta_b,
                 uint32_t *d_n_irregular, cudaStream_t stream);
+// One traversal of a batch: packed pass, byte pass, chain fix-up (those that have work).  d_counters: 4 x u64 scratch
+// ([0],[1] work cursors, [2] chunks re-traversed by k_fixup, [3] irregular-read count of the device packer).
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_counters,
                     cudaStream_t stream);
 

@@ -1,4 +1,4 @@
-// query.cu -- host driver of the query path: read packing, device batches, the pinned double-buffered
+// query.cu -- host driver of the query path: read packing, device batches, the pinned multi-slot
 // streaming pipeline and multi-GPU read sharding.
 //
 // Replaces the per-read loop of src/pml_query.cpp:74-86 (`while (patterns.read()) tbl.query_pml(...)`).

@@ -9,7 +9,8 @@
 // target, whichever that lane needs -- so divergent lanes never serialise extra gathers behind each other and the
 // SM keeps (resident warps x 32) independent gathers in flight to cover DRAM/L2 latency.  Lanes that finish a read
 // pull the next one from a global cursor (one warp-aggregated atomic), so reads of any length mix freely.
-// Outputs are staged in registers and written as aligned 16-byte (PML) / 8-byte (CID) vectors.
+// Outputs are staged per lane in shared memory (64 positions) and written as 64-byte bursts of aligned 16-byte vectors;
+// reads long enough to dominate a batch are cut into speculative chunk tasks and repaired by k_fixup (colbwt_core.cuh).
 #include "internal.h"
 
 namespace colbwt {

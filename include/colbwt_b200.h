@@ -95,7 +95,7 @@ void colbwt_index_free(colbwt_index *idx);
 
 /* n_reads reads: bytes seqs[off[i] .. off[i+1]).  pml has off[n_reads] elements of `pml_width` bytes, cid has
  * off[n_reads] bytes.  Reads are packed on the host (2 bit/base; reads with a byte outside ACGT travel as
- * bytes), streamed through pinned double-buffered copies, traversed on the GPU(s) and the results copied back
+ * bytes), streamed through pinned multi-buffered copies (6 chunks in flight per GPU), traversed on the GPU(s) and the results copied back
  * in input order.  With several devices, chunks of reads are dealt round-robin; no inter-GPU communication. */
 int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                  void *pml, int pml_width, uint8_t *cid);

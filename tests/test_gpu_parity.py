@@ -79,7 +79,7 @@ def test_mixed_batch_regular_and_irregular_reads_keep_input_order(cb, small_inde
 
 
 def test_streaming_chunks_and_pinned_buffers(cb, small_index, monkeypatch):
-    """Many small chunks through the 3-slot pipeline, pageable and pinned output buffers."""
+    """Many small chunks through the multi-slot pipeline, pageable and pinned output buffers."""
     monkeypatch.setenv("COLBWT_CHUNK_BASES", "20000")
     seqs, off = small_index["seqs"], small_index["off"]
     want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
