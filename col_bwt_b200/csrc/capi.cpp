@@ -288,16 +288,19 @@ extern "C" void colbwt_index_free(colbwt_index *idx)
 // pml_query.cpp:79-85: fs << '>' << id << " \n"; std::copy(..., ostream_iterator<size_t>(fs, " ")); fs << "\n";
 extern "C" size_t colbwt_format_stats(char *buf, size_t cap, const char *id, size_t id_len, const void *values, int width, uint64_t m)
 {
-    // exact size first
-    size_t need = 1 + id_len + 2 + 1;
     auto value_at = [&](uint64_t i) -> uint32_t {
         return width == 1 ? ((const uint8_t *)values)[i] : width == 2 ? ((const uint16_t *)values)[i] : ((const uint32_t *)values)[i];
     };
-    for (uint64_t i = 0; i < m; ++i) {
-        uint32_t v = value_at(i);
-        need += (v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10) + 1;
+    // a buffer that holds the worst case (3 / 5 / 10 digits + blank per value) needs no counting pass
+    const size_t worst = 1 + id_len + 2 + 1 + (size_t)m * (width == 1 ? 4 : width == 2 ? 6 : 11);
+    if (!buf || cap < worst) {
+        size_t need = 1 + id_len + 2 + 1;
+        for (uint64_t i = 0; i < m; ++i) {
+            uint32_t v = value_at(i);
+            need += (v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10) + 1;
+        }
+        if (!buf || cap < need) return need;
     }
-    if (!buf || cap < need) return need;
     char *p = buf;
     *p++ = '>';
     memcpy(p, id, id_len);

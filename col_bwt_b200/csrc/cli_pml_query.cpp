@@ -5,9 +5,14 @@
 // Unlike the reference (whose main always returns 0 and whose -l path is broken for more than one read,
 // SURVEY.md section 3.1), failures give a non-zero exit code and -l is accepted as a no-op.
 #include <getopt.h>
+#include <algorithm>
 #include <unistd.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,57 +69,115 @@ int main(int argc, char *const argv[])
     FILE *f_pml = fopen(pml_name.c_str(), "wb"), *f_cid = fopen(cid_name.c_str(), "wb");
     if (!f_pml || !f_cid) { fprintf(stderr, "[ERROR]: cannot write %s / %s\n", pml_name.c_str(), cid_name.c_str()); return 1; }
 
-    std::vector<uint8_t> seqs;
-    std::vector<uint64_t> off;
-    std::vector<std::string> ids;
-    std::vector<uint32_t> pml;
-    std::vector<uint8_t> cid;
+    // Reader thread: parses the next batch (gz + FASTA/FASTQ) while this thread queries, formats and writes the current one.
+    struct Batch {
+        std::vector<uint8_t> seqs;
+        std::vector<uint64_t> off;
+        std::vector<std::string> ids;
+    };
+    std::mutex mtx;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<Batch>> queue;
+    bool reader_done = false;
+    std::thread reader_thread([&] {
+        for (;;) {
+            std::unique_ptr<Batch> b(new Batch);
+            const size_t n = reader.next_batch(b->seqs, b->off, b->ids, 256ull << 20, 8ull << 20);
+            std::unique_lock<std::mutex> lk(mtx);
+            cv.wait(lk, [&] { return queue.size() < 2; });
+            if (n) queue.push_back(std::move(b));
+            else reader_done = true;
+            cv.notify_all();
+            if (!n) return;
+        }
+    });
+    // result buffers in pinned memory (grown on demand): colbwt_query then copies device -> host without a staging hop
+    uint8_t *pml = nullptr, *cid = nullptr;
+    size_t pml_cap = 0, cid_cap = 0;
     uint64_t total_bases = 0, total_reads = 0;
+    double t_wait = 0, t_query = 0, t_format = 0, t_write = 0;
     int rc = 0;
-    while (reader.next_batch(seqs, off, ids, 256ull << 20, 8ull << 20)) {
-        pml.resize(seqs.size() + 1);
-        cid.resize(seqs.size() + 1);
-        if (colbwt_query(idx, seqs.data(), off.data(), ids.size(), pml.data(), COLBWT_PML_U32, cid.data()) != COLBWT_OK) {
+    for (;;) {
+        double t = now_s();
+        std::unique_ptr<Batch> bp;
+        {
+            std::unique_lock<std::mutex> lk(mtx);
+            cv.wait(lk, [&] { return !queue.empty() || reader_done; });
+            if (queue.empty()) break;
+            bp = std::move(queue.front());
+            queue.pop_front();
+            cv.notify_all();
+        }
+        t_wait += now_s() - t;
+        t = now_s();
+        const std::vector<uint8_t> &seqs = bp->seqs;
+        const std::vector<uint64_t> &off = bp->off;
+        const std::vector<std::string> &ids = bp->ids;
+        uint64_t max_len = 0;
+        for (size_t i = 0; i + 1 < off.size(); ++i) max_len = std::max(max_len, off[i + 1] - off[i]);
+        const int width = max_len < 256 ? COLBWT_PML_U8 : max_len < 65536 ? COLBWT_PML_U16 : COLBWT_PML_U32;   // fewer bytes over PCIe
+        if ((seqs.size() + 1) * (size_t)width > pml_cap) {
+            colbwt_host_free(pml);
+            pml_cap = (seqs.size() + 1) * (size_t)width;
+            pml = (uint8_t *)colbwt_host_alloc(pml_cap);
+        }
+        if (seqs.size() + 1 > cid_cap) {
+            colbwt_host_free(cid);
+            cid_cap = seqs.size() + 1;
+            cid = (uint8_t *)colbwt_host_alloc(cid_cap);
+        }
+        if (!pml || !cid) {
             fprintf(stderr, "[ERROR]: %s\n", colbwt_last_error());
             rc = 1;
-            break;
         }
+        if (rc == 0 && colbwt_query(idx, seqs.data(), off.data(), ids.size(), pml, width, cid) != COLBWT_OK) {
+            fprintf(stderr, "[ERROR]: %s\n", colbwt_last_error());
+            rc = 1;
+        }
+        if (rc) continue;   // keep draining the reader
+        t_query += now_s() - t;
+        t = now_s();
         // format in parallel slices, write in order
         const int T = (int)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), ids.size() / 256 + 1));
         std::vector<std::string> out_p(T), out_c(T);
         std::vector<std::thread> th;
-        for (int t = 0; t < T; ++t)
-            th.emplace_back([&, t] {
-                const size_t a = ids.size() * t / T, b = ids.size() * (t + 1) / T;
-                std::string &sp = out_p[t], &sc = out_c[t];
-                for (size_t i = a; i < b; ++i) {
+        for (int t2 = 0; t2 < T; ++t2)
+            th.emplace_back([&, t2] {
+                const size_t a = ids.size() * t2 / T, b = ids.size() * (t2 + 1) / T;
+                std::string &sp = out_p[t2], &sc = out_c[t2];
+                for (size_t i = a; i < b; ++i) {   // append with worst-case room, then trim: one pass per value
                     const uint64_t m = off[i + 1] - off[i];
-                    size_t need = colbwt_format_stats(nullptr, 0, ids[i].data(), ids[i].size(), pml.data() + off[i], 4, m);
                     size_t at = sp.size();
-                    sp.resize(at + need);
-                    colbwt_format_stats(&sp[at], need, ids[i].data(), ids[i].size(), pml.data() + off[i], 4, m);
-                    need = colbwt_format_stats(nullptr, 0, ids[i].data(), ids[i].size(), cid.data() + off[i], 1, m);
+                    sp.resize(at + ids[i].size() + 4 + m * 11);
+                    sp.resize(at + colbwt_format_stats(&sp[at], sp.size() - at, ids[i].data(), ids[i].size(), pml + off[i] * width, width, m));
                     at = sc.size();
-                    sc.resize(at + need);
-                    colbwt_format_stats(&sc[at], need, ids[i].data(), ids[i].size(), cid.data() + off[i], 1, m);
+                    sc.resize(at + ids[i].size() + 4 + m * 4);
+                    sc.resize(at + colbwt_format_stats(&sc[at], sc.size() - at, ids[i].data(), ids[i].size(), cid + off[i], 1, m));
                 }
             });
         for (auto &x : th) x.join();
-        for (int t = 0; t < T; ++t) {
-            fwrite(out_p[t].data(), 1, out_p[t].size(), f_pml);
-            fwrite(out_c[t].data(), 1, out_c[t].size(), f_cid);
+        t_format += now_s() - t;
+        t = now_s();
+        for (int t2 = 0; t2 < T; ++t2) {
+            fwrite(out_p[t2].data(), 1, out_p[t2].size(), f_pml);
+            fwrite(out_c[t2].data(), 1, out_c[t2].size(), f_cid);
         }
+        t_write += now_s() - t;
         total_bases += seqs.size();
         total_reads += ids.size();
     }
+    reader_thread.join();
+    colbwt_host_free(pml);
+    colbwt_host_free(cid);
     fclose(f_pml);
     fclose(f_cid);
     colbwt_index_free(idx);
     if (rc) { unlink(pml_name.c_str()); unlink(cid_name.c_str()); return rc; }   // col-bwt.py:70-77 deletes outputs on failure
     const double dt = now_s() - t1;
     printf("\t[INFO]: Query Complete\n\t[INFO]: Elapsed time (s): %g\n", dt);
-    if (verbose) printf("\t[LOG]: %llu reads, %llu bases, %.3f Mbases/s end to end\n", (unsigned long long)total_reads,
-                        (unsigned long long)total_bases, total_bases / dt / 1e6);
+    if (verbose)
+        printf("\t[LOG]: %llu reads, %llu bases, %.3f Mbases/s end to end (waiting for the parser %.2f s, query %.2f s, formatting %.2f s, writing %.2f s)\n",
+               (unsigned long long)total_reads, (unsigned long long)total_bases, total_bases / dt / 1e6, t_wait, t_query, t_format, t_write);
     printf("\t[INFO]: PMLs written to: %s\n\t[INFO]: CIDs written to: %s\n[INFO]: Done\n", pml_name.c_str(), cid_name.c_str());
     return 0;
 }

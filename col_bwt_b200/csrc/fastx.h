@@ -9,6 +9,7 @@
 #include <zlib.h>
 
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -50,6 +51,26 @@ private:
     }
     static bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
+    // Appends the rest of the current line (without the newline) to `out` using memchr over the buffer; returns the
+    // terminating character ('\n', or -1 at end of file).
+    int rest_of_line(std::vector<uint8_t> &out)
+    {
+        for (;;) {
+            if (beg_ >= end_) {
+                if (eof_) return -1;
+                end_ = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+                beg_ = 0;
+                if (end_ <= 0) { eof_ = true; end_ = 0; return -1; }
+            }
+            const char *p = buf_.data() + beg_;
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end_ - beg_));
+            const size_t k = nl ? (size_t)(nl - p) : (size_t)(end_ - beg_);
+            out.insert(out.end(), (const uint8_t *)p, (const uint8_t *)p + k);
+            beg_ += (int)k + (nl ? 1 : 0);
+            if (nl) return '\n';
+        }
+    }
+
     bool read_record(std::vector<uint8_t> &seqs, std::vector<std::string> &ids)
     {
         int c;
@@ -61,26 +82,35 @@ private:
         std::string id;
         while ((c = getc_()) != -1 && !is_space(c)) id.push_back((char)c);
         if (c == -1) return false;   // kseq: a header cut off by EOF is not a record
-        if (c != '\n') while ((c = getc_()) != -1 && c != '\n') {}   // comment
+        if (c != '\n') { scratch_.clear(); rest_of_line(scratch_); }   // comment
         const size_t start = seqs.size();
         while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
             if (c == '\n') continue;
             const size_t line = seqs.size();
             seqs.push_back((uint8_t)c);
-            while ((c = getc_()) != -1 && c != '\n') seqs.push_back((uint8_t)c);
+            rest_of_line(seqs);
             if (seqs.size() - line > 1 && seqs.back() == '\r') seqs.pop_back();
         }
         if (c == '>' || c == '@') last_ = c;
         else last_ = 0;
         if (c == '+') {   // FASTQ: skip the rest of the '+' line, then as many quality bytes as bases
-            while ((c = getc_()) != -1 && c != '\n') {}
+            scratch_.clear();
+            rest_of_line(scratch_);
             size_t q = 0, want = seqs.size() - start;
-            while (q < want && (c = getc_()) != -1) if (c != '\n' && c != '\r') ++q;
+            while (q < want) {
+                scratch_.clear();
+                const int e = rest_of_line(scratch_);
+                size_t n = scratch_.size();
+                if (n && scratch_.back() == '\r') --n;
+                q += n;
+                if (e == -1) break;
+            }
         }
         ids.push_back(std::move(id));
         return true;
     }
 
+    std::vector<uint8_t> scratch_;
     gzFile fp_;
     std::vector<char> buf_;
     int beg_ = 0, end_ = 0, last_ = 0;

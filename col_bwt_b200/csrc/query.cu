@@ -362,7 +362,13 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     CB_CUDA(cudaSetDevice(dt.device));
     const uint64_t n_bases = off[n_reads] - off[0];
     uint64_t n_words = 0;
-    for (uint64_t i = 0; i < n_reads; ++i) n_words += words_of(off[i + 1] - off[i]);
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        if (off[i + 1] - off[i] >= 0xFFFFFFFFull) {
+            set_error("colbwt_batch_upload: a read of 2^32-1 or more bases is not supported");
+            return COLBWT_ERR_ARG;
+        }
+        n_words += words_of(off[i + 1] - off[i]);
+    }
     if (n_words >= (1ull << 32)) {
         set_error("colbwt_batch_upload: batch too large (packed words do not fit 32-bit offsets); split it");
         return COLBWT_ERR_ARG;
@@ -595,6 +601,10 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
     if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     uint32_t max_len = 0;
     for (uint64_t i = 0; i < n_reads; ++i) max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
+    if (max_len == 0xFFFFFFFFu) {
+        set_error("a read of 2^32-1 or more bases is not supported");
+        return COLBWT_ERR_ARG;
+    }
     if (int rc = check_width(pml_width, max_len)) return rc;
     // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read at a time and
     // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
