@@ -48,6 +48,7 @@ EXPORTS = {
     "colbwt_index_from_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "colbwt_index_from_primaries": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "colbwt_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "colbwt_col_split": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "colbwt_index_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "colbwt_index_free": (None, [C.c_void_p]),
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
@@ -244,6 +245,16 @@ class ColPml:
             self._h = None
 
     __del__ = close
+
+
+def col_split(prefix: str, mode: str = "tunnels", split_rate: int = 10, device: int = 0):
+    """`col_split PREFIX -m MODE -s RATE` (src/col_split.cpp) on the GPU: writes PREFIX.col_runs / PREFIX.col_ids.
+    Returns (set bits of col_runs, bits with a non-zero chain id)."""
+    if mode not in ("tunnels", "all"):
+        raise ValueError("mode must be 'tunnels' or 'all'")     # col_split.cpp:34-46
+    a, b = C.c_uint64(), C.c_uint64()
+    _check(_L.colbwt_col_split(os.fsencode(prefix), int(mode == "all"), split_rate, device, C.byref(a), C.byref(b)), "colbwt_col_split")
+    return a.value, b.value
 
 
 def format_stats(read_id: str, values: np.ndarray) -> bytes:

@@ -11,6 +11,7 @@
  *                            include/common/common.hpp:318-323)
  *   colbwt_index_from_primaries / colbwt_index_save
  *                            src/build_col_bwt.cpp:8-64 (constructors + serialize), on the GPU
+ *   colbwt_col_split         src/col_split.cpp + include/col_split.hpp (+ FL_table.hpp), on the GPU
  *   colbwt_index_stats       col_bwt::bwt_stats / runs / size        include/col_bwt.hpp:331-344
  *   colbwt_query             col_pml::query_pml(const char*, size_t) include/col_bwt.hpp:409-412, for a whole
  *                            batch of reads (the per-read loop of src/pml_query.cpp:74-86)
@@ -87,6 +88,13 @@ int colbwt_index_from_primaries(const char *prefix, const int *devices, int n_de
 /* Write the table as `.col_pml` (col_bwt::serialize, include/col_bwt.hpp:360-370 + LF_table.hpp:325-342): byte-identical
  * to what the reference's build_col_bwt writes for the same primaries. */
 int colbwt_index_save(const colbwt_index *idx, const char *path);
+
+/* Multi-MUM sub-run marking on the GPU: reads PREFIX.bwt.heads, PREFIX.bwt.len and PREFIX.col_mums, writes
+ * PREFIX.col_runs (sdsl bit_vector) and PREFIX.col_ids exactly as the reference's `col_split PREFIX -m MODE -s RATE`
+ * (src/col_split.cpp:62-141, include/col_split.hpp:54-157, walking include/ds/FL_table.hpp) does -- without the
+ * intermediate PREFIX.FL_table.  mode_all = 0: `-m tunnels`, 1: `-m all`; overlap handling is the reference's default
+ * (`append`).  Optional outputs: number of set bits of col_runs, number of them with a non-zero chain id. */
+int colbwt_col_split(const char *prefix, int mode_all, int split_rate, int device, uint64_t *n_set_bits, uint64_t *n_marked);
 
 int colbwt_index_stats(const colbwt_index *idx, colbwt_stats *out);
 void colbwt_index_free(colbwt_index *idx);

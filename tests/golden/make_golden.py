@@ -65,7 +65,7 @@ def pan4(tmp, name="pan4", mode="tunnels", rate="4"):
     run(os.path.join(REF, "build_FL"), p)
     run(os.path.join(REF, "col_split"), p, "-m", mode, "-s", rate)
     # the primaries as the reference tools leave them: inputs of colbwt_index_from_primaries
-    for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_runs", ".col_ids"):
+    for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_runs", ".col_ids", ".col_mums"):
         shutil.copy(p + ext, os.path.join(OUT, name + ".fa" + ext))
     n, pos = F.read_bit_vector(p + ".col_runs")           # col_split writes a plain bit_vector ...
     F.write_shim_sd_vector(p + ".col_runs", n, pos)        # ... build_col_bwt loads an sd_vector

@@ -416,3 +416,40 @@ def test_two_threads_share_one_index(cb, small_index):
     [t.join() for t in ts]
     for pml, cid in results:
         assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("case,mode,rate", [("pan4", "tunnels", 4), ("pan4all", "all", 2)])
+def test_col_split_on_gpu_matches_reference_col_split(cb, golden_dir, tmp_path, case, mode, rate):
+    """colbwt_col_split (GPU FL walks + host overlap sweep) writes the same .col_runs / .col_ids, byte for byte, as the
+    reference's build_FL + col_split wrote for the same .bwt.heads/.bwt.len/.col_mums (tests/golden/make_golden.py)."""
+    import shutil
+    for ext in (".bwt.heads", ".bwt.len", ".col_mums"):
+        shutil.copy(os.path.join(golden_dir, case + ".fa" + ext), tmp_path / ("x.fa" + ext))
+    bits, marked = cb.col_split(str(tmp_path / "x.fa"), mode, rate)
+    for ext in (".col_runs", ".col_ids"):
+        assert (tmp_path / ("x.fa" + ext)).read_bytes() == open(os.path.join(golden_dir, case + ".fa" + ext), "rb").read(), ext
+    ids = np.fromfile(os.path.join(golden_dir, case + ".fa.col_ids"), np.uint8)
+    assert bits == ids.size and marked == int((ids > 0).sum())
+    # the CLI form
+    os.remove(tmp_path / "x.fa.col_runs")
+    r = subprocess.run([os.path.join(ROOT, "col_bwt_b200", "bin", "col_split_b200"), str(tmp_path / "x.fa"), "-m", mode, "-s", str(rate)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "x.fa.col_runs").read_bytes() == open(os.path.join(golden_dir, case + ".fa.col_runs"), "rb").read()
+
+
+def test_col_split_on_gpu_at_scale_and_whole_build_chain(cb, small_index, tmp_path):
+    """primaries + multi-MUMs -> colbwt_col_split -> colbwt_index_from_primaries == the tooling's table (itself pinned to
+    the reference tools), i.e. the in-tree part of `col-bwt build` end to end on the GPU."""
+    idx = small_index["idx"]
+    p = str(tmp_path / "s.fa")
+    PL.write_reference_inputs(p, idx)                      # .bwt.heads .bwt.len .thr_pos .col_mums
+    bits, marked = cb.col_split(p, "tunnels", 5)
+    n, pos = F.read_bit_vector(p + ".col_runs")
+    ids = np.fromfile(p + ".col_ids", np.uint8)
+    assert np.array_equal(pos, idx["split_pos"]) and np.array_equal(ids, idx["split_ids"])
+    tbl = cb.ColPml.from_primaries(p)
+    tbl.save(p + ".col_pml")
+    assert open(p + ".col_pml", "rb").read() == open(small_index["path"], "rb").read()
+    with pytest.raises(cb.ColBwtError):
+        cb.col_split(str(tmp_path / "missing.fa"))
