@@ -364,7 +364,12 @@ def main():
     sampler.active.clear()
     e2e_value = world * n_bases / e2e_s
     e2e_parity = bool(np.array_equal(h_pml.array[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(h_cid.array[: int(off[k])], want[1]))
-    h2d = int(((np.diff(off).astype(np.int64) + 15) // 16).sum() * 4 + 16 * n_reads)
+    # bytes copied host -> device per step: per-read records + 2-bit words, or the raw bytes when the library packs on the
+    # device (its rule: fewer than 4 packing threads for this process and short reads, query.cu)
+    threads_per_rank = int(os.environ.get("COLBWT_HOST_THREADS", max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    dp_env = os.environ.get("COLBWT_DEVICE_PACK")
+    device_pack = (int(dp_env) != 0 if dp_env is not None else threads_per_rank < 4) and max_len < 8192
+    h2d = int(16 * n_reads + (n_bases if device_pack else ((np.diff(off).astype(np.int64) + 15) // 16).sum() * 4))
     d2h = n_bases * (width + 1)
     sampler.stop_flag.set()
 
@@ -407,7 +412,8 @@ def main():
                    "l2": "no flush needed: table + per-step outputs exceed the 126 MB L2" if table_bytes + d2h > (200 << 20) else "working set fits L2 (small workload)",
                    "mismatch_step_frac": round(mismatch_frac, 4), "cid_nonzero_frac": round(cid_frac, 4)},
         "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s,
-                "pml_bytes": width, "api": "colbwt_query (host pinned buffers; host 2-bit packing inside the timed region)"},
+                "pml_bytes": width, "packing": "device" if device_pack else "host",
+                "api": "colbwt_query (host pinned buffers; read packing inside the timed region)"},
         "gpu_launches": batch.launches * a.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "parity_vs_oracle": {"kernel": parity, "e2e": e2e_parity, "reads_checked": k, "checker": kind,
