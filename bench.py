@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("COLBWT_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the workload's)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--check-reads", type=int, default=2000, help="reads compared with the CPU checker after the timed runs (0 = every read)")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
@@ -328,9 +329,10 @@ def main():
 
     # ---- parity spot check against the oracle (not timed; checker only) ------------------------------------------
     pml_d, cid_d = batch.download()
-    k = min(n_reads, 2000)
+    k = n_reads if a.check_reads <= 0 else min(n_reads, a.check_reads)
     ref, kind = cpu_reference(path)
-    want = ref.query_batch(seqs[: int(off[k])], off[: k + 1])
+    want = (ref.query_batch(seqs[: int(off[k])], off[: k + 1], threads=os.cpu_count() or 1) if kind == "reference"
+            else ref.query_batch(seqs[: int(off[k])], off[: k + 1]))
     parity = bool(np.array_equal(pml_d[: int(off[k])].astype(np.uint32), want[0]) and np.array_equal(cid_d[: int(off[k])], want[1]))
     # size-independent invariants on a large slice of the measured output: PML[j] is 0 or PML[j+1]+1
     # inside a read, and never exceeds the bases left of the read
