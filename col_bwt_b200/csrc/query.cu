@@ -587,8 +587,28 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
 
 } // namespace colbwt
 
+static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid);
+
 extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                             void *pml, int pml_width, uint8_t *cid)
+{
+    const int rc = query_impl(idx, seqs, off, n_reads, pml, pml_width, cid);
+    if (rc != COLBWT_OK && rc != COLBWT_ERR_ARG && idx && idx->pipeline) {
+        // a failed copy or launch may leave chunks in flight: wait, then drop the staging pipeline so that the next
+        // call starts from a clean one
+        std::lock_guard<std::mutex> guard(idx->query_mutex);
+        for (auto &d : idx->dev) {
+            cudaSetDevice(d.device);
+            cudaDeviceSynchronize();
+        }
+        cudaGetLastError();
+        destroy_pipeline(idx->pipeline);
+        idx->pipeline = nullptr;
+    }
+    return rc;
+}
+
+static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid)
 {
     if (!idx || !off || !pml || !cid || idx->dev.empty()) {
         set_error("colbwt_query: bad argument");

@@ -58,3 +58,19 @@ def test_compute_calls_fail_loudly_without_gpu(golden_dir):
     cli = os.path.join(ROOT, "col_bwt_b200", "bin", "pml_query_b200")
     r = subprocess.run([cli, os.path.join(golden_dir, "toy"), "-p", os.path.join(golden_dir, "toy_reads.fa")], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU path" in r.stderr
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """`bench.py --impl reference` (the CPU arm of the driver contract) on the toy workload: exactly one JSON line on
+    stdout, whatever libraries print elsewhere, with the keys the contract names."""
+    import json
+    import sys
+    env = dict(os.environ, COLBWT_BENCH_CACHE=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1", "--warmup", "0",
+                        "--cpu-seconds", "0.5"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "bases/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
