@@ -45,12 +45,17 @@ WORKLOADS = {
 }
 for _s in (1, 100):   # configs[3]: sub-sample sweep on the 32-haplotype index (tunnel marking; `all` mode is covered by golden fixtures)
     WORKLOADS[f"c4_s{_s}"] = dict(WORKLOADS["c2"], split_rate=_s)
+for _s in (1, 10, 100):   # non-tunnel marking: marks come from the product's own GPU col_split (-m all), table from from_primaries
+    WORKLOADS[f"c4_all_s{_s}"] = dict(WORKLOADS["c2"], split_rate=_s, mode="all")
 WORKLOADS["c5small"] = dict(synthetic_rows=250_000_000, mean_len=16.0, reads=10_000_000, read_len=150, sub=0.01)
 WORKLOADS["tiny"] = dict(H=4, G=50_000, snp=1e-3, indel=0.0, reads=5_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False)
 WORKLOAD_TEXT = {
     "tiny": "4-haplotype x 50 kbp toy (CPU self-test of bench.py only)",
     "c4_s1": "configs[3]: the configs[1] pangenome marked with tunnels -s 1 (densest chain ids), 10M x 150 bp reads",
     "c4_s100": "configs[3]: the configs[1] pangenome marked with tunnels -s 100 (sparsest chain ids), 10M x 150 bp reads",
+    "c4_all_s1": "configs[3]: the configs[1] pangenome marked with `-m all -s 1` by colbwt_col_split, 10M x 150 bp reads",
+    "c4_all_s10": "configs[3]: the configs[1] pangenome marked with `-m all -s 10` by colbwt_col_split, 10M x 150 bp reads",
+    "c4_all_s100": "configs[3]: the configs[1] pangenome marked with `-m all -s 100` by colbwt_col_split, 10M x 150 bp reads",
     "c5small": "configs[4] scaled to 2.5e8 directly synthesised move rows (4 GB packed table, DRAM-resident), 10M x 150 bp LF-walk reads, 1% substitutions",
     "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
@@ -129,7 +134,17 @@ def build_workload(name: str, device: str, verbose: bool):
         t0 = time.time()
         haps = P.make_haplotypes(w["G"], w["H"], snp=w["snp"], indel=w["indel"], seed=1, tree=w["tree"])
         idx = PL.build_index(haps, with_revcomp=True, split_rate=w.get("split_rate", 10), min_mum=20, device=device, verbose=verbose)
-        PL.write_col_pml(stem + ".col_pml", idx["columns"])
+        if w.get("mode") == "all":
+            # the tooling only marks tunnels; `-m all` comes from the product's GPU build chain on the same primaries
+            import col_bwt_b200 as cb
+            PL.write_reference_inputs(stem + ".fa", idx)
+            cb.col_split(stem + ".fa", "all", w.get("split_rate", 10))
+            t = cb.ColPml.from_primaries(stem + ".fa")
+            t.save(stem + ".col_pml")
+            idx["columns"] = {"n": t.n, "ch": np.zeros(t.r, np.uint8), "bwt_r": t.bwt_r, "col_id": np.zeros(int(t.stats.marked_rows), np.uint8) + 1}
+            t.close()
+        else:
+            PL.write_col_pml(stem + ".col_pml", idx["columns"])
         np.save(stem + ".text.npy", idx["text"])
         np.save(stem + ".seq_starts.npy", idx["seq_starts"])
         cols = idx["columns"]
