@@ -195,6 +195,24 @@ uint64_t emu_fastx(const char *path, uint64_t max_bases, uint64_t max_reads, uin
     return n;
 }
 
+// Chunk planner (tasks.h) for one read: writes lo, hi, top, slot per task (by_slot order); returns the task count.
+uint32_t emu_plan(uint32_t len, uint32_t chunk, uint32_t warm, uint32_t *out, uint32_t cap)
+{
+    SplitParams sp;
+    sp.chunk = chunk;
+    sp.warm = warm;
+    TaskPlan plan;
+    plan.add_read(1000, 7, len, true, sp);
+    plan.finish();
+    for (size_t i = 0; i < plan.by_slot.size() && i < cap; ++i) {
+        out[4 * i] = plan.by_slot[i].lo;
+        out[4 * i + 1] = plan.by_slot[i].hi;
+        out[4 * i + 2] = plan.by_slot[i].top;
+        out[4 * i + 3] = plan.by_slot[i].slot;
+    }
+    return (uint32_t)plan.by_slot.size();
+}
+
 int emu_pack(const uint8_t *seq, uint64_t len, uint32_t *words) { return pack_read_2bit(seq, len, words) ? 1 : 0; }
 uint64_t emu_slow_rows(EmuTable *t) { return t->slow_rows; }
 uint32_t emu_flags(EmuTable *t) { return t->flags; }

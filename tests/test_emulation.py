@@ -202,3 +202,24 @@ def test_long_reads_chunk_tasks_with_chain_verification_are_exact(small_index, e
                 assert np.array_equal(p0, p1) and np.array_equal(c0, c1), (chunk, warm, narrow, width)
         redone[(chunk, warm)] = emu.redone / max(1, emu.tasks)
     assert redone[(64, 0)] > 0.9 and redone[(256, 256)] < 0.5 * redone[(64, 16)]
+
+
+@pytest.mark.parametrize("length,chunk,warm", [(8192, 4096, 512), (8193, 4096, 512), (100000, 4096, 512), (70000, 64, 16), (129, 64, 0), (5000, 4096, 9999)])
+def test_chunk_planner_tiles_the_read(length, chunk, warm):
+    """tasks.h: chunks are listed top first, tile [0, len) exactly, are balanced, and never warm up past the read."""
+    import ctypes as C
+    from emu import SO, build
+    build()
+    L = C.CDLL(SO)
+    L.emu_plan.restype = C.c_uint32
+    L.emu_plan.argtypes = [C.c_uint32] * 3 + [C.c_void_p, C.c_uint32]
+    out = np.zeros(4 * 4096, np.uint32)
+    n = L.emu_plan(length, chunk, warm, out.ctypes.data, 4096)
+    t = out[: 4 * n].reshape(n, 4)
+    assert n == -(-length // chunk)
+    assert t[0, 1] == length and t[0, 2] == length                       # top chunk: no warm-up, starts from the true state
+    assert t[-1, 0] == 0
+    assert (t[1:, 1] == t[:-1, 0]).all()                                 # contiguous, descending
+    assert (t[:, 1] > t[:, 0]).all() and (t[:, 1] - t[:, 0]).max() - (t[:, 1] - t[:, 0]).min() <= n
+    assert (t[1:, 2] == np.minimum(length, t[1:, 1] + warm)).all()
+    assert (t[:, 3] == np.arange(n)).all()
