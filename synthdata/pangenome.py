@@ -153,7 +153,8 @@ def sample_reads(text: np.ndarray, seq_starts: np.ndarray, n_reads: int, read_le
 
 
 def sample_reads_device(text, seq_starts: np.ndarray, n_reads: int, read_len: int, *, sub: float = 0.01, ins: float = 0.0,
-                        dele: float = 0.0, seed: int = 2, len_sigma: float = 0.0, device="cuda", chunk_bases: int = 1 << 28):
+                        dele: float = 0.0, seed: int = 2, len_sigma: float = 0.0, device="cuda", chunk_bases: int = 1 << 28,
+                        return_origin: bool = False):
     """torch version of sample_reads for bench-scale batches (1e9+ bases), generated on `device` in chunks.
 
     Error model: every output base advances the source position by 1 (plain), 0 (insertion: the base is random) or
@@ -181,6 +182,8 @@ def sample_reads_device(text, seq_starts: np.ndarray, n_reads: int, read_len: in
     code_of = torch.zeros(256, dtype=torch.long, device=dev)
     code_of[acgt.long()] = torch.arange(4, device=dev)
     off_host = offsets.cpu().numpy()
+    origin_seq = np.empty(n_reads, dtype=np.int64)
+    origin_pos = np.empty(n_reads, dtype=np.int64)
     r0 = 0
     while r0 < n_reads:
         r1 = int(np.searchsorted(off_host, off_host[r0] + chunk_bases, side="right")) - 1
@@ -209,5 +212,9 @@ def sample_reads_device(text, seq_starts: np.ndarray, n_reads: int, read_len: in
         rot = torch.randint(1, 4, (nb,), generator=g, device=dev)
         b = torch.where(is_sub, acgt[(code_of[b.long()] + rot) & 3], b)
         out[off_host[r0]:off_host[r1]] = b.cpu().numpy()
+        origin_seq[r0:r1] = which.cpu().numpy()
+        origin_pos[r0:r1] = (start - ss[which]).cpu().numpy()
         r0 = r1
+    if return_origin:   # (sequence index, offset of the read's first base inside it): experiments on read ordering
+        return out, off_host.astype(np.uint64), origin_seq, origin_pos
     return out, off_host.astype(np.uint64)
