@@ -321,6 +321,7 @@ def main():
     n_reads, n_bases = off.size - 1, int(off[-1])
     max_len = int(np.diff(off).max())
     width = cb.PML_U8 if max_len < 256 else (cb.PML_U16 if max_len < 65536 else cb.PML_U32)
+    width = max(width, int(os.environ.get("COLBWT_BENCH_PML_WIDTH", "0")))   # development: measure a wider PML type
     pml_dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width]
 
     tbl = cb.ColPml.load(path, devices=[local])

@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcolbwt_b200.so")
+LIB_PATH = os.environ.get("COLBWT_LIB") or os.path.join(_HERE, "libcolbwt_b200.so")   # COLBWT_LIB: development builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

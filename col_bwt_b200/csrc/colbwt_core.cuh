@@ -273,7 +273,9 @@ template <typename PmlT> struct Lane {
     uint32_t slot = NO_SLOT;
     uint32_t rw = 0;        // current packed word
     uint64_t out_base = 0;
-    uint32_t hi_slot = 64;  // highest valid slot of the output block being staged (64 = nothing staged yet)
+    uint32_t hi_slot = 64;  // highest valid slot of the output block being staged (>= block size: nothing staged yet)
+    CB_HD static PmlT plen_type() { return PmlT(); }   // lets generic test code name PmlT
+    uint32_t flush = 0;     // deferred flush request (warp-cooperative flush in k_traverse): 0 = none, else highest slot + 1
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -285,28 +287,47 @@ template <typename PmlT> struct Lane {
 // ---------------------------------------------------------------------------------------------------------
 struct Stage {
     uint32_t *base;     // this thread's word 0
-    uint32_t stride;    // words between consecutive words of one thread (CTA size on the device, 1 on the host)
+    uint32_t stride;    // words between consecutive words of one thread
+    uint32_t swz;       // word w lives at index w ^ swz (< 16): k_traverse keeps each lane's block contiguous and rotates
+                        // it by the lane number, so that 32 lanes touching the same word number hit different banks
 };
-constexpr uint32_t STAGE_BLOCK = 64;
-constexpr uint32_t STAGE_CID_WORDS = STAGE_BLOCK / 4;
-template <typename PmlT> constexpr uint32_t stage_words() { return STAGE_CID_WORDS + (sizeof(PmlT) < 4 ? STAGE_BLOCK * (uint32_t)sizeof(PmlT) / 4 : 0); }
+// Positions staged per lane.  The stage competes with the L1 for the SM's 256 KB, and the L1 is what holds the row
+// gathers in flight and the line a fast-forward step re-reads: with 4 x 256 lanes per SM, 32 KB of stage per CTA leaves
+// a 124 KB L1 (49.8 Gbases/s on C2), 34 KB pushes the carve-out to the next step and leaves 92 KB (42.0), a full
+// carve-out 28 KB (24.2) -- profiles/r1/l1_capacity_probe.log, stage_sweep.log.  So 64 positions with 8-bit PML
+// (64 + 64 bytes per lane), 32 with 16-bit PML (32 + 64 bytes), 16 with 32-bit PML (16 + 64 bytes).
+#ifndef COLBWT_STAGE_BLOCK_U16
+#define COLBWT_STAGE_BLOCK_U16 32
+#endif
+#ifndef COLBWT_STAGE_BLOCK_U32
+#define COLBWT_STAGE_BLOCK_U32 16
+#endif
+template <typename PmlT> CB_HD constexpr uint32_t stage_block()
+{
+    return sizeof(PmlT) == 1 ? 64 : (sizeof(PmlT) == 2 ? COLBWT_STAGE_BLOCK_U16 : COLBWT_STAGE_BLOCK_U32);
+}
+template <typename PmlT> CB_HD constexpr uint32_t stage_cid_words() { return stage_block<PmlT>() / 4; }
+template <typename PmlT> CB_HD constexpr uint32_t stage_words() { return stage_cid_words<PmlT>() + stage_block<PmlT>() * (uint32_t)sizeof(PmlT) / 4; }
 
-CB_HD uint32_t &stage_word(const Stage &sg, uint32_t w) { return sg.base[w * sg.stride]; }
+// Bank rotation mask of a lane's block (see Stage::swz): the rotation must stay inside the block.
+template <typename PmlT> CB_HD constexpr uint32_t stage_swz_mask() { return ((stage_words<PmlT>() & (0u - stage_words<PmlT>())) - 1u) & 15u; }
+
+CB_HD uint32_t &stage_word(const Stage &sg, uint32_t w) { return sg.base[(w ^ sg.swz) * sg.stride]; }
 
 // Write slots [lo, hi] of one staged array (element size ES bytes, first word w0) to dst (= address of slot 0).
-template <int ES> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *dst, uint32_t lo, uint32_t hi)
+template <int ES, uint32_t BLOCK> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *dst, uint32_t lo, uint32_t hi)
 {
     constexpr uint32_t PER_VEC = 16 / ES;                       // slots per 16-byte vector
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-    if (lo == 0 && hi == STAGE_BLOCK - 1) {                     // complete block: one straight burst
+    if (lo == 0 && hi == BLOCK - 1) {                     // complete block: one straight burst
 #pragma unroll
-        for (uint32_t q = 0; q < STAGE_BLOCK / PER_VEC; ++q)
+        for (uint32_t q = 0; q < BLOCK / PER_VEC; ++q)
             st_v4(dst + q * 16, stage_word(sg, w0 + 4 * q), stage_word(sg, w0 + 4 * q + 1), stage_word(sg, w0 + 4 * q + 2), stage_word(sg, w0 + 4 * q + 3));
         return;
     }
 #endif
 #pragma unroll
-    for (uint32_t q = 0; q < STAGE_BLOCK / PER_VEC; ++q) {
+    for (uint32_t q = 0; q < BLOCK / PER_VEC; ++q) {
         const uint32_t s0 = q * PER_VEC, s1 = s0 + PER_VEC - 1;
         if (s1 < lo || s0 > hi) continue;
         const uint32_t w = w0 + q * 4;
@@ -324,7 +345,8 @@ template <int ES> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *
             for (uint32_t sl = a; sl <= e; ++sl) {
                 const uint32_t v = stage_word(sg, w0 + sl * ES / 4) >> (8 * ((sl * ES) & 3));
                 if (ES == 1) dst[sl] = (uint8_t)v;
-                else reinterpret_cast<uint16_t *>(dst)[sl] = (uint16_t)v;
+                else if (ES == 2) reinterpret_cast<uint16_t *>(dst)[sl] = (uint16_t)v;
+                else reinterpret_cast<uint32_t *>(dst)[sl] = v;
             }
         }
     }
@@ -332,25 +354,65 @@ template <int ES> CB_HD void stage_write(const Stage &sg, uint32_t w0, uint8_t *
 
 template <typename PmlT> CB_HD void lane_flush(Lane<PmlT> &L, const Stage &sg, const BatchView &bv, uint64_t g)
 {
-    const uint32_t lo = (uint32_t)(g & (STAGE_BLOCK - 1));
+    constexpr uint32_t BLOCK = stage_block<PmlT>(), CIDW = stage_cid_words<PmlT>();
+    const uint32_t lo = (uint32_t)(g & (BLOCK - 1));
     const uint64_t blk = g - lo;
-    stage_write<1>(sg, 0, bv.cid + blk, lo, L.hi_slot);
-    if (sizeof(PmlT) == 1) stage_write<1>(sg, STAGE_CID_WORDS, reinterpret_cast<uint8_t *>(bv.pml) + blk, lo, L.hi_slot);
-    else if (sizeof(PmlT) == 2) stage_write<2>(sg, STAGE_CID_WORDS, reinterpret_cast<uint8_t *>(bv.pml) + 2 * blk, lo, L.hi_slot);
-    L.hi_slot = STAGE_BLOCK - 1;                                // the next block below starts full-width
+    stage_write<1, BLOCK>(sg, 0, bv.cid + blk, lo, L.hi_slot);
+    if (sizeof(PmlT) == 1) stage_write<1, BLOCK>(sg, CIDW, reinterpret_cast<uint8_t *>(bv.pml) + blk, lo, L.hi_slot);
+    else if (sizeof(PmlT) == 2) stage_write<2, BLOCK>(sg, CIDW, reinterpret_cast<uint8_t *>(bv.pml) + 2 * blk, lo, L.hi_slot);
+    else stage_write<4, BLOCK>(sg, CIDW, reinterpret_cast<uint8_t *>(bv.pml) + 4 * blk, lo, L.hi_slot);
+    L.hi_slot = BLOCK - 1;                                // the next block below starts full-width
 }
 
-template <typename PmlT>
+// Warp-cooperative flush (k_traverse): a lane that completes a block only posts a request (Lane::flush) and the whole
+// warp then moves the block, one 32-bit word per thread -- word w of the flushing lane's stage goes to its place in
+// CID (w < 16) or PML -- instead of one thread walking through ~230 instructions while 31 wait.  `block` = word 0 of
+// the flushing lane's stage (contiguous words, rotated by swz as in Stage), [lo, hi] = valid slots, blk = global position of slot 0.  Words cut by
+// the edge of a read are written element by element (the neighbouring elements belong to another read).
+template <typename PmlT> CB_HD void flush_word(const uint32_t *block, uint32_t swz, uint32_t w, const BatchView &bv, uint64_t blk, uint32_t lo, uint32_t hi)
+{
+    if (w >= stage_words<PmlT>()) return;
+    const bool is_cid = w < stage_cid_words<PmlT>();
+    const uint32_t es = is_cid ? 1u : (uint32_t)sizeof(PmlT), per = 4u / es;
+    const uint32_t s0 = (is_cid ? w : w - stage_cid_words<PmlT>()) * per, s1 = s0 + per - 1;
+    if (s1 < lo || s0 > hi) return;
+    uint8_t *dst = is_cid ? bv.cid + blk + s0 : reinterpret_cast<uint8_t *>(bv.pml) + (blk + s0) * es;
+    const uint32_t v = block[w ^ swz];
+    if (s0 >= lo && s1 <= hi) {
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint32_t *>(dst) = v;
+#else
+        for (uint32_t b = 0; b < 4; ++b) dst[b] = (uint8_t)(v >> (8 * b));
+#endif
+        return;
+    }
+    for (uint32_t e = 0; e < per; ++e) {
+        if (s0 + e < lo || s0 + e > hi) continue;
+        if (es == 1) dst[e] = (uint8_t)(v >> (8 * e));
+        else if (es == 2) reinterpret_cast<uint16_t *>(dst)[e] = (uint16_t)(v >> (16 * e));
+        else *reinterpret_cast<uint32_t *>(dst) = v;
+    }
+}
+
+template <bool DEFER = false, typename PmlT>
 CB_HD void lane_emit(Lane<PmlT> &L, const Stage &sg, const BatchView &bv, uint32_t jj, uint32_t plen, uint32_t cid)   // jj < emit_top
 {
+    constexpr uint32_t BLOCK = stage_block<PmlT>(), CIDW = stage_cid_words<PmlT>();
     const uint64_t g = L.out_base + jj;
-    const uint32_t slot = (uint32_t)(g & (STAGE_BLOCK - 1));
-    if (L.hi_slot >= STAGE_BLOCK) L.hi_slot = slot;             // first output of this read / chunk
+    const uint32_t slot = (uint32_t)(g & (BLOCK - 1));
+    if (L.hi_slot >= BLOCK) L.hi_slot = slot;             // first output of this read / chunk
     reinterpret_cast<uint8_t *>(&stage_word(sg, slot >> 2))[slot & 3] = (uint8_t)cid;
-    if (sizeof(PmlT) == 1) reinterpret_cast<uint8_t *>(&stage_word(sg, STAGE_CID_WORDS + (slot >> 2)))[slot & 3] = (uint8_t)plen;
-    else if (sizeof(PmlT) == 2) reinterpret_cast<uint16_t *>(&stage_word(sg, STAGE_CID_WORDS + (slot >> 1)))[slot & 1] = (uint16_t)plen;
-    else reinterpret_cast<uint32_t *>(bv.pml)[g] = plen;
-    if (slot == 0 || jj == L.j_stop) lane_flush(L, sg, bv, g);
+    if (sizeof(PmlT) == 1) reinterpret_cast<uint8_t *>(&stage_word(sg, CIDW + (slot >> 2)))[slot & 3] = (uint8_t)plen;
+    else if (sizeof(PmlT) == 2) reinterpret_cast<uint16_t *>(&stage_word(sg, CIDW + (slot >> 1)))[slot & 1] = (uint16_t)plen;
+    else stage_word(sg, CIDW + slot) = plen;
+    if (slot == 0 || jj == L.j_stop) {
+        if (DEFER) {
+            L.flush = L.hi_slot + 1;                            // the warp writes [slot, hi_slot] of this block after the step
+            L.hi_slot = BLOCK - 1;
+        } else {
+            lane_flush(L, sg, bv, g);
+        }
+    }
 }
 
 // Start read `m` on this lane (zero-length reads are skipped by the caller).
@@ -366,7 +428,7 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin(Lane<PmlT> &L, const
     L.slot = NO_SLOT;
     L.in_off = m.in_off;
     L.out_base = m.out_off;
-    L.hi_slot = STAGE_BLOCK;
+    L.hi_slot = stage_block<PmlT>();
     if (PACKED) L.rw = ld_ro(bv.words + m.in_off + ((m.len - 1) >> 4));
 }
 
@@ -383,7 +445,7 @@ template <bool PACKED, typename PmlT> CB_HD void lane_begin_task(Lane<PmlT> &L, 
     L.slot = k.slot;
     L.in_off = k.in_off;
     L.out_base = k.out_off;
-    L.hi_slot = STAGE_BLOCK;
+    L.hi_slot = stage_block<PmlT>();
     if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.top - 1) >> 4));
 }
 
@@ -401,12 +463,12 @@ CB_HD void lane_begin_from_state(Lane<PmlT> &L, const BatchView &bv, const Chunk
     L.slot = k.slot;
     L.in_off = k.in_off;
     L.out_base = k.out_off;
-    L.hi_slot = STAGE_BLOCK;
+    L.hi_slot = stage_block<PmlT>();
     if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.hi - 1) >> 4));
 }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
-template <bool PACKED, typename PmlT>
+template <bool PACKED, bool DEFER = false, typename PmlT>
 CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, const Row row, const uint8_t *code_lut)
 {
     const uint32_t len = row_len(row);
@@ -453,7 +515,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const B
     } else {
         L.plen = 0;                              // col_bwt.hpp:520-523
     }
-    if (jj < L.emit_top) lane_emit(L, sg, bv, jj, L.plen, cid);
+    if (jj < L.emit_top) lane_emit<DEFER>(L, sg, bv, jj, L.plen, cid);
     if (jj == L.j_stop && L.slot == NO_SLOT) {   // whole read: the reference's last LF step has no observable effect
         L.state = LANE_IDLE;
         return;
@@ -498,7 +560,7 @@ CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const B
 
 
 // Narrow-layout twin of lane_step.  `w` = hot[addr], or cold[addr] when the lane is in LANE_COLD.
-template <bool PACKED, typename PmlT>
+template <bool PACKED, bool DEFER = false, typename PmlT>
 CB_HD void lane_step_narrow(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, const uint64_t w, const uint8_t *code_lut)
 {
     const uint32_t st = L.state & 7u;
@@ -572,7 +634,7 @@ CB_HD void lane_step_narrow(Lane<PmlT> &L, const Stage &sg, const TableView &t, 
     if (!PACKED && code >= CODE_OTHER)
         match = (code == CODE_OTHER) && (chc == CHC_OTHER) && (ld_ro(t.ch8 + L.addr) == cbyte);
     L.plen = match ? L.plen + 1 : 0;
-    if (jj < L.emit_top) lane_emit(L, sg, bv, jj, L.plen, cid);
+    if (jj < L.emit_top) lane_emit<DEFER>(L, sg, bv, jj, L.plen, cid);
     if (jj == L.j_stop && L.slot == NO_SLOT) {
         L.state = LANE_IDLE;
         return;

@@ -9,8 +9,10 @@
 // target, whichever that lane needs -- so divergent lanes never serialise extra gathers behind each other and the
 // SM keeps (resident warps x 32) independent gathers in flight to cover DRAM/L2 latency.  Lanes that finish a read
 // pull the next one from a global cursor (one warp-aggregated atomic), so reads of any length mix freely.
-// Outputs are staged per lane in shared memory (64 positions) and written as 64-byte bursts of aligned 16-byte vectors;
+// Outputs are staged per lane in shared memory (64 positions) and written by the whole warp as 64-byte bursts;
 // reads long enough to dominate a batch are cut into speculative chunk tasks and repaired by k_fixup (colbwt_core.cuh).
+#include <atomic>
+
 #include "internal.h"
 
 namespace colbwt {
@@ -21,14 +23,14 @@ template <bool PACKED, typename PmlT, int CTAS, bool NARROW>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
-    __shared__ uint8_t code_lut[256];
-    extern __shared__ uint32_t stage_mem[];                     // stage_words<PmlT>() words per thread, thread-interleaved
-    if (!PACKED) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) code_lut[i] = code_lut_g[i];
-        __syncthreads();
-    }
-    const Stage sg{stage_mem + threadIdx.x, TRAVERSE_THREADS};
+    extern __shared__ uint32_t stage_mem[];                     // stage_words<PmlT>() words per thread: its output block
+    const uint8_t *code_lut = code_lut_g;                       // byte reads only; 256 bytes that stay in the L1 (no static
+                                                                // shared memory: it would push the carve-out up a step)
+    constexpr uint32_t STAGE_PITCH = stage_words<PmlT>();
     const uint32_t lane = threadIdx.x & 31;
+    // each lane's block is contiguous (the warp flushes it with 32 consecutive words) and rotated by the lane number
+    const Stage sg{stage_mem + threadIdx.x * STAGE_PITCH, 1, lane & stage_swz_mask<PmlT>()};
+    const uint32_t *warp_stage = stage_mem + (threadIdx.x - lane) * STAGE_PITCH;
     const ReadMeta *meta = PACKED ? bv.meta : bv.meta_b;
     const ChunkTask *tasks = PACKED ? bv.tasks : bv.tasks + bv.n_tasks;
     const uint32_t n_tasks = PACKED ? bv.n_tasks : bv.n_tasks_b;       // chunk tasks of split reads go first (longest work)
@@ -68,11 +70,31 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
             if (NARROW) {
                 const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t.cold : t.hot;
                 const uint64_t w = ld_row64(base + L.addr);
-                lane_step_narrow<PACKED>(L, sg, t, bv, w, code_lut);
+                lane_step_narrow<PACKED, true>(L, sg, t, bv, w, code_lut);
             } else {
                 const Row row = ld_row(t.rows + L.addr);
-                lane_step<PACKED>(L, sg, t, bv, row, code_lut);
+                lane_step<PACKED, true>(L, sg, t, bv, row, code_lut);
             }
+        }
+        // ---- completed output blocks: the warp writes them together (colbwt_core.cuh: flush_word) -------------------
+        uint32_t fl = __ballot_sync(0xffffffffu, L.flush != 0);
+        if (fl) {
+            const uint64_t g = L.out_base + L.j;                // position of the base just emitted (lowest slot of the block)
+            const uint32_t mine = (uint32_t)(g & (stage_block<PmlT>() - 1)) | (L.flush << 8);
+            const uint64_t my_blk = g & ~(uint64_t)(stage_block<PmlT>() - 1);
+            L.flush = 0;
+            __syncwarp();
+            do {
+                const int src = __ffs(fl) - 1;
+                fl &= fl - 1;
+                const uint64_t blk = __shfl_sync(0xffffffffu, my_blk, src);
+                const uint32_t lh = __shfl_sync(0xffffffffu, mine, src);
+                const uint32_t *block = warp_stage + src * STAGE_PITCH;
+#pragma unroll
+                for (uint32_t w = 0; w < stage_words<PmlT>(); w += 32)
+                    flush_word<PmlT>(block, (uint32_t)src & stage_swz_mask<PmlT>(), w + lane, bv, blk, lh & 255u, (lh >> 8) - 1u);
+            } while (fl);
+            __syncwarp();
         }
     }
 }
@@ -127,7 +149,7 @@ __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchVie
     __shared__ uint32_t stage_mem[128 * stage_words<PmlT>()];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) code_lut[i] = code_lut_g[i];
     __syncthreads();
-    const Stage sg{stage_mem + threadIdx.x, 128};
+    const Stage sg{stage_mem + threadIdx.x, 128, 0};
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= bv.n_chains) return;
     const ChainDesc d = bv.chains[c];
@@ -135,10 +157,45 @@ __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchVie
     if (n) atomicAdd(redone, (unsigned long long)n);
 }
 
-// 4 CTAs of 256 lanes per SM (48-56 registers, no spills): the measured optimum on DRAM-resident tables -- more lanes in
-// flight only thrash the L2 (profiles/r1/variant_sweep2.log; re-measured with the output staging: 3/4/5/6 CTAs = 40.9 /
-// 44.8 / 39.3 / 23.1 Gbases/s on C2) -- and what the output staging (up to 48 KB per CTA) allows.
+// 4 CTAs of 256 lanes per SM (42-48 registers, no spills).  More resident lanes do not help: 5 or 6 CTAs give the same
+// rate when the L1 is kept large (stage of 32 positions) and half of it when their shared memory squeezes the L1
+// (profiles/r1/stage_sweep.log) -- the kernel sits on the DRAM random-line rate.  The shared-memory carve-out is set
+// explicitly to the smallest size that holds the 4 CTAs: left to itself the driver sizes it for the occupancy the
+// register count would allow and takes the difference from the L1 (42.0 instead of 49.8 Gbases/s on C2).
 constexpr int TRAVERSE_CTAS = 4;
+
+static int carveout_percent(size_t smem_per_cta /* dynamic + static */, int ctas, int device)
+{
+    int per_sm = 0, reserved = 0;
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, device);
+    const size_t need = (size_t)ctas * (smem_per_cta + (size_t)reserved);
+    static const size_t steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};   // sm_100 carve-out sizes
+    size_t pick = (size_t)per_sm;
+    for (size_t kb : steps_kb)
+        if (kb * 1024 >= need) { pick = std::min(pick, kb * 1024); break; }
+    // the hint is a percentage of the maximum and the driver rounds it UP to the next size (58 % = 132.2 KB became 164 KB
+    // under ncu), so round down here: 57 % -> 132 KB, 43 % -> 100 KB
+    return (int)(pick >= (size_t)per_sm ? 100 : pick * 100 / (size_t)per_sm);
+}
+
+template <bool PACKED, typename PmlT, bool NARROW>
+static int launch_variant(unsigned grid, size_t smem, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut, unsigned long long *cursor, cudaStream_t stream)
+{
+    auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, NARROW>;
+    static std::atomic<uint64_t> configured{0};   // per instantiation: devices whose function attributes are set
+    const uint64_t bit = 1ull << (dt.device & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncAttributes fa;
+        CB_CUDA(cudaFuncGetAttributes(&fa, kern));
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem + fa.sharedSizeBytes, TRAVERSE_CTAS, dt.device)));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    kern<<<grid, TRAVERSE_THREADS, smem, stream>>>(dt.view, bv, lut, cursor);
+    return COLBWT_OK;
+}
+
 template <bool PACKED, typename PmlT>
 static int launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut,
                       unsigned long long *cursor, cudaStream_t stream)
@@ -147,17 +204,9 @@ static int launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const
                                                       : ((uint64_t)reads + (PACKED ? bv.n_tasks : bv.n_tasks_b) + TRAVERSE_THREADS - 1) / TRAVERSE_THREADS;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * TRAVERSE_CTAS));
     const size_t smem = (size_t)TRAVERSE_THREADS * stage_words<PmlT>() * sizeof(uint32_t);
-    const bool narrow = dt.view.hot != nullptr;   // built only when COLBWT_NARROW=1 (index.cu)
-    if (narrow) {
-        auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, true>;
-        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TRAVERSE_THREADS, smem, stream>>>(dt.view, bv, lut, cursor);
-    } else {
-        auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, false>;
-        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TRAVERSE_THREADS, smem, stream>>>(dt.view, bv, lut, cursor);
-    }
-    return COLBWT_OK;
+    if (dt.view.hot != nullptr)   // narrow layout, built only when COLBWT_NARROW=1 (index.cu)
+        return launch_variant<PACKED, PmlT, true>(grid, smem, dt, bv, lut, cursor, stream);
+    return launch_variant<PACKED, PmlT, false>(grid, smem, dt, bv, lut, cursor, stream);
 }
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)
@@ -251,18 +300,25 @@ k_gather_bench(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t loads
     if (acc == 0x12345678u) sink[0] = acc;
 }
 
-template <bool DEP> static void launch_gather(int variant, unsigned grid, const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint32_t *sink)
+template <bool DEP, int V> static void launch_gather_v(unsigned grid, size_t smem, const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint32_t *sink)
+{
+    auto kern = k_gather_bench<DEP, V>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem>>>(buf, n_sectors, per_thread, sink);
+}
+
+template <bool DEP> static void launch_gather(int variant, unsigned grid, size_t smem, const uint4 *buf, uint64_t n_sectors, uint32_t per_thread, uint32_t *sink)
 {
     switch (variant) {
-    case 1: k_gather_bench<DEP, 1><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 2: k_gather_bench<DEP, 2><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 3: k_gather_bench<DEP, 3><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 4: k_gather_bench<DEP, 4><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 5: k_gather_bench<DEP, 5><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 6: k_gather_bench<DEP, 6><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 7: k_gather_bench<DEP, 7><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    case 8: k_gather_bench<DEP, 8><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
-    default: k_gather_bench<DEP, 0><<<grid, 256>>>(buf, n_sectors, per_thread, sink); break;
+    case 1: launch_gather_v<DEP, 1>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 2: launch_gather_v<DEP, 2>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 3: launch_gather_v<DEP, 3>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 4: launch_gather_v<DEP, 4>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 5: launch_gather_v<DEP, 5>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 6: launch_gather_v<DEP, 6>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 7: launch_gather_v<DEP, 7>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    case 8: launch_gather_v<DEP, 8>(grid, smem, buf, n_sectors, per_thread, sink); break;
+    default: launch_gather_v<DEP, 0>(grid, smem, buf, n_sectors, per_thread, sink); break;
     }
 }
 
@@ -293,7 +349,11 @@ extern "C" int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, i
     CB_CUDA(cudaMalloc(&buf, n_sectors * 32));
     CB_CUDA(cudaMalloc(&sink, 4));
     k_fill<<<prop.multiProcessorCount * 8, 256>>>(buf, n_sectors * 2);
-    const unsigned grid = prop.multiProcessorCount * 8;
+    // probe knobs: CTAs (of 256 lanes) resident per SM and dynamic shared memory per CTA -- shared memory comes out of the
+    // same 256 KB as the L1, whose lines hold the gathers in flight
+    const int gb_ctas = getenv("COLBWT_GB_CTAS") ? std::max(1, std::min(8, atoi(getenv("COLBWT_GB_CTAS")))) : 8;
+    const size_t gb_smem = getenv("COLBWT_GB_SMEM") ? (size_t)atoi(getenv("COLBWT_GB_SMEM")) : 0;
+    const unsigned grid = prop.multiProcessorCount * gb_ctas;
     const uint64_t threads = (uint64_t)grid * 256;
     const uint32_t per_thread = (uint32_t)std::max<uint64_t>(1, loads / threads);
     cudaEvent_t e0, e1;
@@ -302,8 +362,8 @@ extern "C" int colbwt_gather_bench(int device, uint64_t bytes, uint64_t loads, i
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {   // first repetition is the warm-up
         CB_CUDA(cudaEventRecord(e0));
-        if (dependent & 1) launch_gather<true>(dependent >> 8, grid, buf, n_sectors, per_thread, sink);
-        else launch_gather<false>(dependent >> 8, grid, buf, n_sectors, per_thread, sink);
+        if (dependent & 1) launch_gather<true>(dependent >> 8, grid, gb_smem, buf, n_sectors, per_thread, sink);
+        else launch_gather<false>(dependent >> 8, grid, gb_smem, buf, n_sectors, per_thread, sink);
         CB_CUDA(cudaEventRecord(e1));
         CB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

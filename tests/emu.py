@@ -15,10 +15,15 @@ HDR2 = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "tasks.h")
 HDR3 = os.path.join(HERE, "..", "col_bwt_b200", "csrc", "fastx.h")
 
 
+EXTRA = os.environ.get("COLBWT_EMU_CXXFLAGS", "").split()   # e.g. -DCOLBWT_STAGE_BLOCK=32 (development variants)
+if EXTRA:
+    SO = SO[:-3] + "_" + "".join(ch for ch in "".join(EXTRA) if ch.isalnum()) + ".so"
+
+
 def build():
     newest = max(os.path.getmtime(p) for p in SRC + [HDR, HDR2, HDR3])
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRC + ["-lz"], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + EXTRA + SRC + ["-lz"], check=True)
 
 
 class Emu:
@@ -75,11 +80,12 @@ class Emu:
         self.tasks = nt.value
         return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]
 
-    def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False):
+    def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False, defer=False):
+        """defer: post flush requests and serve them with flush_word, as the warps of k_traverse do."""
         seqs = np.ascontiguousarray(seqs, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
         pml = np.zeros(seqs.size + 8, {1: np.uint8, 2: np.uint16, 4: np.uint32}[pml_width])
         cid = np.zeros(seqs.size + 8, np.uint8)
         self.iters = self.L.emu_query(self.h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data,
-                                      pml_width, cid.ctypes.data, int(force_bytes) | (2 if narrow else 0))
+                                      pml_width, cid.ctypes.data, int(force_bytes) | (2 if narrow else 0) | (4 if defer else 0))
         return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]

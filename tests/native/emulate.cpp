@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 
 #include "../../col_bwt_b200/csrc/colbwt_core.cuh"
@@ -44,7 +45,7 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
     bv.cid = cid;
     bv.bytes = seqs;
     uint32_t stage_buf[64] = {0};
-    const Stage sg{stage_buf, 1};
+    const Stage sg{stage_buf, 1, 0};
     std::vector<uint32_t> words;
     std::vector<uint64_t> word_off(n_reads, 0);
     std::vector<char> is_packed(n_reads, 0);
@@ -233,10 +234,11 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
                    uint8_t *cid, int force_bytes)
 {
     const bool narrow = (force_bytes & 2) != 0;
+    const bool defer = (force_bytes & 4) != 0;   // bit 2: post flush requests and serve them word by word (flush_word), as the warp does
     force_bytes &= 1;
     uint64_t iters = 0;
     uint32_t stage_buf[64] = {0};
-    const Stage sg{stage_buf, 1};
+    const Stage sg{stage_buf, 1, defer ? 5u : 0u};   // deferred mode also exercises the bank rotation
     BatchView bv{};
     bv.pml = pml;
     bv.cid = cid;
@@ -252,13 +254,22 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
         auto run = [&](auto &L, auto packed_tag) {
             constexpr bool P = decltype(packed_tag)::value;
             lane_begin<P>(L, t->view, bv, m);
+            using PmlT = std::remove_reference_t<decltype(L.plen_type())>;
             while (L.state != LANE_IDLE) {
                 if (narrow) {
                     const uint64_t *base = ((L.state & 7u) == LANE_COLD) ? t->view.cold : t->view.hot;
-                    lane_step_narrow<P>(L, sg, t->view, bv, base[L.addr], t->code_lut);
+                    if (defer) lane_step_narrow<P, true>(L, sg, t->view, bv, base[L.addr], t->code_lut);
+                    else lane_step_narrow<P>(L, sg, t->view, bv, base[L.addr], t->code_lut);
                 } else {
                     if (g_trace_on) g_trace.push_back(L.addr);
-                    lane_step<P>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                    if (defer) lane_step<P, true>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                    else lane_step<P>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                }
+                if (L.flush) {   // what k_traverse's warp does after the step, one "thread" at a time
+                    const uint64_t g = L.out_base + L.j;
+                    for (uint32_t w = 0; w < 64; ++w)
+                        flush_word<PmlT>(stage_buf, sg.swz, w, bv, g & ~(uint64_t)(stage_block<PmlT>() - 1), (uint32_t)(g & (stage_block<PmlT>() - 1)), L.flush - 1);
+                    L.flush = 0;
                 }
                 ++iters;
             }
