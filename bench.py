@@ -408,6 +408,10 @@ def main():
                 "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
                 "gather": {"table_bytes": table_bytes, "random_sector_rate_per_s": s_rand, "dependent_sector_rate_per_s": s_dep,
                            "frac_of_random_sector_rate": round(per_gpu_bases_s / s_rand, 4)}}
+    if roofline["traffic"]:   # what the DRAM actually moved (ncu capture of this workload) at this run's launch time
+        dram_gbs = roofline["traffic"] / (ms_per_step * 1e-3) / 1e9
+        roofline["dram"] = {"gbs": round(dram_gbs, 1), "frac_of_peak": round(dram_gbs / peak, 4),
+                            "note": "every L2 miss of a 16-byte row gather fills a 128-byte line (DESIGN.md section 4)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------------------------
     cpu = None
