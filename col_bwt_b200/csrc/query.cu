@@ -363,6 +363,10 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     const uint64_t n_bases = off[n_reads] - off[0];
     uint64_t n_words = 0;
     for (uint64_t i = 0; i < n_reads; ++i) {
+        if (off[i + 1] < off[i]) {
+            set_error("colbwt_batch_upload: offsets must be non-decreasing (read %llu)", (unsigned long long)i);
+            return COLBWT_ERR_ARG;
+        }
         if (off[i + 1] - off[i] >= 0xFFFFFFFFull) {
             set_error("colbwt_batch_upload: a read of 2^32-1 or more bases is not supported");
             return COLBWT_ERR_ARG;
@@ -620,7 +624,17 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     uint64_t chunk_bases = 48ull << 20;
     if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     uint32_t max_len = 0;
-    for (uint64_t i = 0; i < n_reads; ++i) max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        if (off[i + 1] < off[i]) {
+            set_error("colbwt_query: offsets must be non-decreasing (read %llu)", (unsigned long long)i);
+            return COLBWT_ERR_ARG;
+        }
+        max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
+    }
+    if (!seqs && total_bases) {
+        set_error("colbwt_query: null sequence buffer");
+        return COLBWT_ERR_ARG;
+    }
     if (max_len == 0xFFFFFFFFu) {
         set_error("a read of 2^32-1 or more bases is not supported");
         return COLBWT_ERR_ARG;

@@ -184,6 +184,16 @@ def test_error_codes(cb, tmp_path, golden_dir):
     with pytest.raises(cb.ColBwtError) as e:
         cb.ColPml.from_rows(rows, cols["bwt_r"], cols["n"])
     assert e.value.code == -3
+    # malformed batches are refused, not traversed
+    tbl = cb.ColPml.load(os.path.join(golden_dir, "toy"))
+    seqs = np.frombuffer(b"ACGTACGTAC", np.uint8)
+    for call in (lambda: tbl.query(seqs, np.array([0, 6, 4, 10], np.uint64)),
+                 lambda: tbl.batch(seqs, np.array([0, 6, 4, 10], np.uint64))):
+        with pytest.raises(cb.ColBwtError) as e:
+            call()
+        assert e.value.code == -5 and "non-decreasing" in str(e.value)
+    p, c = tbl.query(seqs, np.array([0, 4, 4, 10], np.uint64))    # an empty read in the middle is fine
+    assert p.size == 10
 
 
 def test_cli_is_a_drop_in_for_pml_query(golden_dir, tmp_path):
