@@ -49,6 +49,7 @@ EXPORTS = {
     "colbwt_index_from_primaries": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "colbwt_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "colbwt_col_split": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "colbwt_rlbwt_to_bwt": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),
     "colbwt_index_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "colbwt_index_free": (None, [C.c_void_p]),
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
@@ -255,6 +256,14 @@ def col_split(prefix: str, mode: str = "tunnels", split_rate: int = 10, device: 
     a, b = C.c_uint64(), C.c_uint64()
     _check(_L.colbwt_col_split(os.fsencode(prefix), int(mode == "all"), split_rate, device, C.byref(a), C.byref(b)), "colbwt_col_split")
     return a.value, b.value
+
+
+def rlbwt_to_bwt(prefix: str, device: int = 0) -> int:
+    """`rlbwt_to_bwt PREFIX` (src/rlbwt_to_bwt.cpp:8-34) on the GPU: PREFIX.bwt.heads + PREFIX.bwt.len -> PREFIX.bwt.
+    Returns the number of characters written."""
+    n = C.c_uint64()
+    _check(_L.colbwt_rlbwt_to_bwt(os.fsencode(prefix), device, C.byref(n)), "colbwt_rlbwt_to_bwt")
+    return n.value
 
 
 def format_stats(read_id: str, values: np.ndarray) -> bytes:

@@ -12,6 +12,7 @@
  *   colbwt_index_from_primaries / colbwt_index_save
  *                            src/build_col_bwt.cpp:8-64 (constructors + serialize), on the GPU
  *   colbwt_col_split         src/col_split.cpp + include/col_split.hpp (+ FL_table.hpp), on the GPU
+ *   colbwt_rlbwt_to_bwt      src/rlbwt_to_bwt.cpp:8-34, on the GPU
  *   colbwt_index_stats       col_bwt::bwt_stats / runs / size        include/col_bwt.hpp:331-344
  *   colbwt_query             col_pml::query_pml(const char*, size_t) include/col_bwt.hpp:409-412, for a whole
  *                            batch of reads (the per-read loop of src/pml_query.cpp:74-86)
@@ -95,6 +96,11 @@ int colbwt_index_save(const colbwt_index *idx, const char *path);
  * intermediate PREFIX.FL_table.  mode_all = 0: `-m tunnels`, 1: `-m all`; overlap handling is the reference's default
  * (`append`).  Optional outputs: number of set bits of col_runs, number of them with a non-zero chain id. */
 int colbwt_col_split(const char *prefix, int mode_all, int split_rate, int device, uint64_t *n_set_bits, uint64_t *n_marked);
+
+/* Run-length BWT -> plain BWT: reads PREFIX.bwt.heads and PREFIX.bwt.len, writes PREFIX.bwt exactly as the reference's
+ * `rlbwt_to_bwt PREFIX` (src/rlbwt_to_bwt.cpp:8-34) does -- each head byte, unmodified, repeated `len` times.
+ * Optional output: the number of bytes written. */
+int colbwt_rlbwt_to_bwt(const char *prefix, int device, uint64_t *n_out);
 
 int colbwt_index_stats(const colbwt_index *idx, colbwt_stats *out);
 void colbwt_index_free(colbwt_index *idx);

@@ -52,6 +52,16 @@ def write_primaries(prefix: str, heads: np.ndarray, lens: np.ndarray, thr: np.nd
     write_u40(prefix + ".thr_pos", thr)
 
 
+def expand_rlbwt(prefix: str) -> np.ndarray:
+    """What the reference's rlbwt_to_bwt writes for prefix.bwt.heads / prefix.bwt.len (src/rlbwt_to_bwt.cpp:24-27): each head
+    byte as it is, `len` times, over the records both files hold."""
+    heads = np.fromfile(prefix + ".bwt.heads", dtype=np.uint8)
+    raw = np.fromfile(prefix + ".bwt.len", dtype=np.uint8)
+    r = min(heads.size, raw.size // 5)
+    lens = u40_unpack(raw[:r * 5].reshape(r, 5))
+    return np.repeat(heads[:r], lens.astype(np.int64))
+
+
 def write_bit_vector(path: str, n: int, positions: np.ndarray) -> None:
     """sdsl::bit_vector layout (u64 bit count, ceil(n/64) u64 words, LSB first)."""
     words = np.zeros((n + 63) // 64, dtype="<u8")

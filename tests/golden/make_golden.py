@@ -65,6 +65,9 @@ def pan4(tmp, name="pan4", mode="tunnels", rate="4"):
     run(os.path.join(REF, "build_FL"), p)
     run(os.path.join(REF, "col_split"), p, "-m", mode, "-s", rate)
     # the primaries as the reference tools leave them: inputs of colbwt_index_from_primaries
+    if name == "pan4":   # plain BWT as the reference's rlbwt_to_bwt expands it (checker of colbwt_rlbwt_to_bwt)
+        run(os.path.join(REF, "rlbwt_to_bwt"), p)
+        shutil.copy(p + ".bwt", os.path.join(OUT, name + ".fa.bwt"))
     for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_runs", ".col_ids", ".col_mums"):
         shutil.copy(p + ext, os.path.join(OUT, name + ".fa" + ext))
     n, pos = F.read_bit_vector(p + ".col_runs")           # col_split writes a plain bit_vector ...

@@ -463,3 +463,45 @@ def test_col_split_on_gpu_at_scale_and_whole_build_chain(cb, small_index, tmp_pa
     assert open(p + ".col_pml", "rb").read() == open(small_index["path"], "rb").read()
     with pytest.raises(cb.ColBwtError):
         cb.col_split(str(tmp_path / "missing.fa"))
+
+
+def test_rlbwt_to_bwt_on_gpu(cb, golden_dir, small_index, tmp_path):
+    """colbwt_rlbwt_to_bwt / rlbwt_to_bwt_b200 write the file the reference's rlbwt_to_bwt writes (golden pan4.fa.bwt), and
+    agree with the pinned restatement (synthdata.formats.expand_rlbwt) on edge cases and on a multi-chunk-sized input."""
+    import shutil
+    p = str(tmp_path / "x.fa")
+    for ext in (".bwt.heads", ".bwt.len"):
+        shutil.copy(os.path.join(golden_dir, "pan4.fa" + ext), p + ext)
+    assert cb.rlbwt_to_bwt(p) == os.path.getsize(os.path.join(golden_dir, "pan4.fa.bwt"))
+    assert open(p + ".bwt", "rb").read() == open(os.path.join(golden_dir, "pan4.fa.bwt"), "rb").read()
+    os.remove(p + ".bwt")
+    r = subprocess.run([os.path.join(ROOT, "col_bwt_b200", "bin", "rlbwt_to_bwt_b200"), p], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(p + ".bwt", "rb").read() == open(os.path.join(golden_dir, "pan4.fa.bwt"), "rb").read()
+    # terminators kept as they are, zero-length runs, a run longer than 65535, surplus length records, lengths not multiple of 16
+    q = str(tmp_path / "e.fa")
+    np.frombuffer(b"A\x00C\x01GTA", np.uint8).tofile(q + ".bwt.heads")
+    F.write_u40(q + ".bwt.len", np.array([3, 1, 0, 2, 70000, 1, 5, 9, 9]))
+    assert cb.rlbwt_to_bwt(q) == 70012
+    assert open(q + ".bwt", "rb").read() == F.expand_rlbwt(q).tobytes()
+    # the synthetic index's runs, and 300 M characters in 40 runs (two 256 MB chunks)
+    idx = small_index["idx"]
+    s = str(tmp_path / "s.fa")
+    F.write_primaries(s, idx["heads"], idx["lens"], idx["thr_run"])
+    assert cb.rlbwt_to_bwt(s) == small_index["cols"]["n"]
+    assert open(s + ".bwt", "rb").read() == F.expand_rlbwt(s).tobytes()
+    b = str(tmp_path / "b.fa")
+    rng = np.random.default_rng(5)
+    np.frombuffer(b"ACGT" * 10, np.uint8).tofile(b + ".bwt.heads")
+    F.write_u40(b + ".bwt.len", rng.integers(1, 15_000_000, 40))
+    n = cb.rlbwt_to_bwt(b)
+    got = np.fromfile(b + ".bwt", np.uint8)
+    assert got.size == n and np.array_equal(got, F.expand_rlbwt(b))
+    # empty and missing inputs
+    e = str(tmp_path / "z.fa")
+    open(e + ".bwt.heads", "wb").close()
+    open(e + ".bwt.len", "wb").close()
+    assert cb.rlbwt_to_bwt(e) == 0 and os.path.getsize(e + ".bwt") == 0
+    with pytest.raises(cb.ColBwtError) as err:
+        cb.rlbwt_to_bwt(str(tmp_path / "missing.fa"))
+    assert err.value.code == -1

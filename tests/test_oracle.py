@@ -49,3 +49,26 @@ def test_oracle_load_rejects_missing_and_short(tmp_path, golden_dir):
     p.write_bytes(data[:100])
     with pytest.raises(OSError):
         oracle.Oracle(str(p))
+
+
+@pytest.mark.parametrize("case", ["toy_rl", "pan4"])
+def test_rlbwt_expansion_matches_reference_rlbwt_to_bwt(golden_dir, tmp_path, case):
+    """synthdata.formats.expand_rlbwt (the checker of colbwt_rlbwt_to_bwt) == the reference's rlbwt_to_bwt, byte for byte:
+    against the committed pan4.fa.bwt fixture, and against the compiled reference tool where it is present."""
+    import shutil
+    import subprocess
+    from synthdata import formats as F
+    p = str(tmp_path / "x.fa")
+    if case == "pan4":
+        for ext in (".bwt.heads", ".bwt.len"):
+            shutil.copy(os.path.join(golden_dir, "pan4.fa" + ext), p + ext)
+        want = open(os.path.join(golden_dir, "pan4.fa.bwt"), "rb").read()
+        assert F.expand_rlbwt(p).tobytes() == want
+    else:   # terminators (0 and 1) are written as they are, zero-length runs write nothing, extra length records are ignored
+        heads = np.frombuffer(b"A\x00C\x01GTA", np.uint8)
+        np.asarray(heads).tofile(p + ".bwt.heads")
+        F.write_u40(p + ".bwt.len", np.array([3, 1, 0, 2, 70000, 1, 5, 9, 9]))
+        assert F.expand_rlbwt(p).tobytes() == b"AAA\x00\x01\x01" + b"G" * 70000 + b"T" + b"A" * 5
+    if oracle.have_ref():
+        subprocess.run([oracle.ref_bin("rlbwt_to_bwt"), p], check=True, stdout=subprocess.DEVNULL)
+        assert open(p + ".bwt", "rb").read() == F.expand_rlbwt(p).tobytes()
