@@ -623,13 +623,27 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     // chunk geometry
     uint64_t chunk_bases = 48ull << 20;
     if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+    // one pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB
     uint32_t max_len = 0;
-    for (uint64_t i = 0; i < n_reads; ++i) {
-        if (off[i + 1] < off[i]) {
-            set_error("colbwt_query: offsets must be non-decreasing (read %llu)", (unsigned long long)i);
+    {
+        const int T = n_reads >= (1u << 16) ? Pool::get().size() : 1;
+        std::vector<uint64_t> part_max((size_t)T, 0), part_bad((size_t)T, UINT64_MAX);
+        Pool::get().parallel_for(T, [&](int t) {
+            const uint64_t a = n_reads * (uint64_t)t / (uint64_t)T, b = n_reads * (uint64_t)(t + 1) / (uint64_t)T;
+            uint64_t mx = 0, bad = UINT64_MAX;
+            for (uint64_t i = a; i < b; ++i) {
+                if (off[i + 1] < off[i]) bad = std::min(bad, i);
+                else mx = std::max(mx, off[i + 1] - off[i]);
+            }
+            part_max[(size_t)t] = mx;
+            part_bad[(size_t)t] = bad;
+        });
+        const uint64_t bad = *std::min_element(part_bad.begin(), part_bad.end());
+        if (bad != UINT64_MAX) {
+            set_error("colbwt_query: offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
             return COLBWT_ERR_ARG;
         }
-        max_len = std::max<uint32_t>(max_len, (uint32_t)std::min<uint64_t>(off[i + 1] - off[i], 0xFFFFFFFFull));
+        max_len = (uint32_t)std::min<uint64_t>(*std::max_element(part_max.begin(), part_max.end()), 0xFFFFFFFFull);
     }
     if (!seqs && total_bases) {
         set_error("colbwt_query: null sequence buffer");
