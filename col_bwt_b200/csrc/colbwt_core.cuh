@@ -296,6 +296,9 @@ struct Stage {
 // a 124 KB L1 (49.8 Gbases/s on C2), 34 KB pushes the carve-out to the next step and leaves 92 KB (42.0), a full
 // carve-out 28 KB (24.2) -- profiles/r1/l1_capacity_probe.log, stage_sweep.log.  So 64 positions with 8-bit PML
 // (64 + 64 bytes per lane), 32 with 16-bit PML (32 + 64 bytes), 16 with 32-bit PML (16 + 64 bytes).
+#ifndef COLBWT_STAGE_BLOCK_U8
+#define COLBWT_STAGE_BLOCK_U8 64
+#endif
 #ifndef COLBWT_STAGE_BLOCK_U16
 #define COLBWT_STAGE_BLOCK_U16 32
 #endif
@@ -304,7 +307,7 @@ struct Stage {
 #endif
 template <typename PmlT> CB_HD constexpr uint32_t stage_block()
 {
-    return sizeof(PmlT) == 1 ? 64 : (sizeof(PmlT) == 2 ? COLBWT_STAGE_BLOCK_U16 : COLBWT_STAGE_BLOCK_U32);
+    return sizeof(PmlT) == 1 ? COLBWT_STAGE_BLOCK_U8 : (sizeof(PmlT) == 2 ? COLBWT_STAGE_BLOCK_U16 : COLBWT_STAGE_BLOCK_U32);
 }
 template <typename PmlT> CB_HD constexpr uint32_t stage_cid_words() { return stage_block<PmlT>() / 4; }
 template <typename PmlT> CB_HD constexpr uint32_t stage_words() { return stage_cid_words<PmlT>() + stage_block<PmlT>() * (uint32_t)sizeof(PmlT) / 4; }

@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(128) k_fixup(const TableView t, const BatchVie
 // (profiles/r1/stage_sweep.log) -- the kernel sits on the DRAM random-line rate.  The shared-memory carve-out is set
 // explicitly to the smallest size that holds the 4 CTAs: left to itself the driver sizes it for the occupancy the
 // register count would allow and takes the difference from the L1 (42.0 instead of 49.8 Gbases/s on C2).
-constexpr int TRAVERSE_CTAS = 4;
+#ifndef COLBWT_TRAVERSE_CTAS
+#define COLBWT_TRAVERSE_CTAS 4
+#endif
+constexpr int TRAVERSE_CTAS = COLBWT_TRAVERSE_CTAS;
 
 static int carveout_percent(size_t smem_per_cta /* dynamic + static */, int ctas, int device)
 {
