@@ -505,3 +505,20 @@ def test_rlbwt_to_bwt_on_gpu(cb, golden_dir, small_index, tmp_path):
     with pytest.raises(cb.ColBwtError) as err:
         cb.rlbwt_to_bwt(str(tmp_path / "missing.fa"))
     assert err.value.code == -1
+
+
+def test_randomised_batches(cb, small_index, monkeypatch):
+    """A short round of tools/fuzz_parity.py: random ragged batches, every legal PML width, random chunk geometry for the
+    long-read path, streaming call and device-resident batch alike -- equal to the oracle on every base."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_parity as fz
+    for k in ("COLBWT_SPLIT", "COLBWT_SPLIT_CHUNK", "COLBWT_SPLIT_WARM", "COLBWT_SPLIT_MIN"):
+        monkeypatch.delenv(k, raising=False)      # restored after the test; one_round sets them freely
+    tbl = cb.ColPml.load(small_index["path"])
+    orc = oracle.Oracle(small_index["path"])
+    rng = np.random.default_rng(7)
+    idx = small_index["idx"]
+    for _ in range(30):
+        ok, info = fz.one_round(cb, tbl, orc, rng, idx["text"], idx["seq_starts"], small_index["haps"])
+        assert ok, info
