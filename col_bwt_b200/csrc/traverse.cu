@@ -9,7 +9,8 @@
 // target, whichever that lane needs -- so divergent lanes never serialise extra gathers behind each other and the
 // SM keeps (resident warps x 32) independent gathers in flight to cover DRAM/L2 latency.  Lanes that finish a read
 // pull the next one from a global cursor (one warp-aggregated atomic), so reads of any length mix freely.
-// Outputs are staged per lane in shared memory (64 positions) and written by the whole warp as 64-byte bursts;
+// Outputs are staged per lane in shared memory (64 / 32 / 16 positions for 8 / 16 / 32-bit PML, sized so that the
+// carve-out leaves the L1 its 124-156 KB) and written by the whole warp as bursts of up to 64 bytes per array;
 // reads long enough to dominate a batch are cut into speculative chunk tasks and repaired by k_fixup (colbwt_core.cuh).
 #include <atomic>
 
