@@ -621,7 +621,7 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     if (n_reads == 0) return COLBWT_OK;
     const uint64_t total_bases = off[n_reads] - off[0];
     // chunk geometry
-    uint64_t chunk_bases = 48ull << 20;
+    uint64_t chunk_bases = 96ull << 20;   // measured on C2 (profiles/r1/e2e_chunk_sweep.log): 16/24/32/48/96/128/192 M -> 83.6/85.0/81.1/76.3/71.8-73.2/72.0/73.1 ms
     if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     // one pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB
     uint32_t max_len = 0;
