@@ -219,8 +219,8 @@ class ColPml:
         seqs, offsets = _as_batch(seqs, offsets)
         total = int(offsets[-1] - offsets[0])
         if out is None:
-            pml = np.zeros(total, _PML_DTYPE[pml_width])
-            cid = np.zeros(total, np.uint8)
+            pml = np.empty(total, _PML_DTYPE[pml_width])   # every base of every read is written by the library
+            cid = np.empty(total, np.uint8)
         else:
             pml, cid = out
             assert pml.dtype.itemsize == pml_width and pml.size >= total and cid.size >= total

@@ -658,6 +658,9 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
     if (!getenv("COLBWT_CHUNK_BASES"))
         chunk_bases = std::max<uint64_t>(chunk_bases, std::min<uint64_t>(512ull << 20, (total_bases / n_reads) * 32768));
+    // pageable result buffers are reached through one pinned staging area per slot: keep each under 256 MB
+    const bool pageable_out = !(is_pinned(pml) && is_pinned(cid));
+    if (pageable_out && !getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / (uint64_t)(pml_width + 1));
     chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
     chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
     // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
@@ -666,9 +669,9 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     const int n_dev = (int)idx->dev.size();
     std::lock_guard<std::mutex> guard(idx->query_mutex);
     Pipeline *plp = nullptr;
-    if (int rc = get_pipeline(idx, chunk_reads, chunk_bases, pml_width, !(is_pinned(pml) && is_pinned(cid)), &plp)) return rc;
+    const bool staged_out = pageable_out;
+    if (int rc = get_pipeline(idx, chunk_reads, chunk_bases, pml_width, staged_out, &plp)) return rc;
     Pipeline &pl = *plp;
-    const bool staged_out = !(is_pinned(pml) && is_pinned(cid));
     // Pack on the device when the input can be DMA-ed as it is (pinned) and no read will be split into chunk tasks:
     // H2D has headroom (the link is busy in the other direction), host cores often do not (one process per GPU).
     const SplitParams sp_query = SplitParams::from_env();
@@ -699,9 +702,16 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
             cudaEventElapsedTime(&ct.end, ev_origin, k.tev[3]);
             timeline.push_back(ct);
         }
-        if (staged_out) {
-            memcpy(pml_out + k.out_base * (uint64_t)pml_width, k.h_out, k.out_bases * (uint64_t)pml_width);
-            memcpy(cid + k.out_base, k.h_out + pl.cap_bases * (uint64_t)pml_width + 32, k.out_bases);
+        if (staged_out) {   // pageable destination: copy out with all packing threads (first-touch page faults included)
+            uint8_t *dst[2] = {pml_out + k.out_base * (uint64_t)pml_width, cid + k.out_base};
+            const uint8_t *src[2] = {k.h_out, k.h_out + pl.cap_bases * (uint64_t)pml_width + 32};
+            const uint64_t bytes[2] = {k.out_bases * (uint64_t)pml_width, k.out_bases};
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)Pool::get().size(), (bytes[0] + bytes[1]) >> 20));
+            Pool::get().parallel_for(2 * T, [&](int i) {
+                const int a = i / T, t = i % T;
+                const uint64_t lo = bytes[a] * (uint64_t)t / (uint64_t)T, hi = bytes[a] * (uint64_t)(t + 1) / (uint64_t)T;
+                memcpy(dst[a] + lo, src[a] + lo, hi - lo);
+            });
         }
         k.pending = false;
         return COLBWT_OK;
