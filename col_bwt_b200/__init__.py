@@ -53,6 +53,7 @@ EXPORTS = {
     "colbwt_index_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "colbwt_index_free": (None, [C.c_void_p]),
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
+    "colbwt_index_last_packing": (C.c_int, [C.c_void_p]),
     "colbwt_host_alloc": (C.c_void_p, [C.c_size_t]),
     "colbwt_host_free": (None, [C.c_void_p]),
     "colbwt_batch_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
@@ -227,6 +228,11 @@ class ColPml:
         _check(_L.colbwt_query(self._h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data, pml_width,
                                cid.ctypes.data), "colbwt_query")
         return pml, cid
+
+    @property
+    def last_packing(self) -> str:
+        """Where the last query() packed the reads: "host" or "device" (the library measures both and keeps the faster)."""
+        return "device" if _L.colbwt_index_last_packing(self._h) == 1 else "host"
 
     def query_pml(self, pattern: bytes | str):
         """col_pml::query_pml(pattern) (col_bwt.hpp:403-412): (PML lengths, chain ids), indexed by read position."""

@@ -45,6 +45,11 @@ struct colbwt_index {
     uint8_t code_lut[256];
     std::mutex query_mutex;                 // one colbwt_query at a time per index
     colbwt::Pipeline *pipeline = nullptr;   // staging buffers + streams, kept between colbwt_query calls
+    // Where colbwt_query packs the reads (query.cu): bases/s of the last large call packed on the host [0] / on the device [1],
+    // the number of large calls so far, and what the last call did.
+    double pack_rate[2] = {0.0, 0.0};
+    uint32_t large_calls = 0;
+    int last_packing = 0;
 };
 
 namespace colbwt {

@@ -670,16 +670,36 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     std::lock_guard<std::mutex> guard(idx->query_mutex);
     Pipeline *plp = nullptr;
     const bool staged_out = pageable_out;
+    const Pipeline *before = idx->pipeline;
     if (int rc = get_pipeline(idx, chunk_reads, chunk_bases, pml_width, staged_out, &plp)) return rc;
+    const bool fresh_pipeline = plp != before;   // this call pays for the staging allocations: not a timing sample
     Pipeline &pl = *plp;
     // Pack on the device when the input can be DMA-ed as it is (pinned) and no read will be split into chunk tasks:
     // H2D has headroom (the link is busy in the other direction), host cores often do not (one process per GPU).
     const SplitParams sp_query = SplitParams::from_env();
     const char *dp_env = getenv("COLBWT_DEVICE_PACK");
-    // Measured on one B200 with 16 host cores: host packing 19.5 Gbases/s end to end, device packing 17.0 (the extra
-    // 1 B/base of H2D slows the D2H stream on the shared link); so the device packs only when this process has fewer
-    // than 4 packing threads (8 ranks on a 16-core box), or when COLBWT_DEVICE_PACK=1 asks for it.
-    const bool device_pack = (dp_env ? atoi(dp_env) != 0 : Pool::get().size() < 4) && is_pinned(seqs) && max_len < sp_query.min_len;
+    // Where to pack is measured, not guessed.  One B200 fed by 16 cores: host 19.5-22.7 Gbases/s end to end, device 17.0 (the
+    // extra 1 B/base of H2D slows the D2H stream on the shared link); two ranks with 8 threads each: 37.7 against 34.8;
+    // with fewer threads per process the host packer (2.6 Gbases/s per thread) falls behind the link.  So: the first large
+    // timed call follows a rule (device iff fewer than 4 packing threads), the next tries the other way once, later calls
+    // take the faster of the two (5 % hysteresis) and re-try the other one every 64th large call.  COLBWT_DEVICE_PACK
+    // pins the choice.
+    const bool can_device_pack = is_pinned(seqs) && max_len < sp_query.min_len;
+    const bool large_call = total_bases >= (64ull << 20);
+    bool device_pack = false;
+    if (dp_env) {
+        device_pack = atoi(dp_env) != 0 && can_device_pack;
+    } else if (can_device_pack) {
+        const int rule = Pool::get().size() < 4 ? 1 : 0;
+        const double *rate = idx->pack_rate;
+        int best = rule;
+        if (rate[0] > 0 && rate[1] > 0) best = rate[1] > 1.05 * rate[0] ? 1 : (rate[0] > 1.05 * rate[1] ? 0 : rule);
+        if (!large_call) device_pack = best != 0;
+        else if (rate[rule] == 0) device_pack = rule != 0;
+        else if (rate[1 - rule] == 0) device_pack = rule == 0;
+        else device_pack = (idx->large_calls % 64 == 63) ? best == 0 : best != 0;
+    }
+    idx->last_packing = device_pack ? 1 : 0;
 
     static const int trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
     struct ChunkTimes { float h2d0, k0, d2h0, end; };
@@ -806,8 +826,14 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
         fprintf(stderr, "[colbwt_query] %llu chunks, %.1f Mbases: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, loop %.1f ms, total %.1f ms (%s outputs, packing on the %s)\n",
                 (unsigned long long)chunk_no, total_bases / 1e6, t_pack * 1e3, t_drain * 1e3, t_enqueue * 1e3, t_loop * 1e3,
                 (now() - t_begin) * 1e3, staged_out ? "staged" : "pinned", device_pack ? "device" : "host");
+    if (large_call && !dp_env && can_device_pack && !fresh_pipeline) {
+        idx->pack_rate[device_pack ? 1 : 0] = (double)total_bases / std::max(1e-9, now() - t_begin);
+        ++idx->large_calls;
+    }
     return COLBWT_OK;
 }
+
+extern "C" int colbwt_index_last_packing(const colbwt_index *idx) { return idx ? idx->last_packing : -1; }
 
 extern "C" void *colbwt_host_alloc(size_t bytes)
 {

@@ -114,6 +114,11 @@ void colbwt_index_free(colbwt_index *idx);
 int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                  void *pml, int pml_width, uint8_t *cid);
 
+/* Where the last colbwt_query on this index packed the reads into 2 bits per base: 0 on the host, 1 on the device (raw
+ * bytes copied as they are; only when `seqs` is pinned and the reads are short).  The library measures both ways on large
+ * calls and keeps the faster one; COLBWT_DEVICE_PACK=0|1 pins the choice.  No reference counterpart (diagnostic). */
+int colbwt_index_last_packing(const colbwt_index *idx);
+
 /* Pinned host memory for seqs / pml / cid buffers (lets colbwt_query copy without a staging hop). */
 void *colbwt_host_alloc(size_t bytes);
 void colbwt_host_free(void *p);
