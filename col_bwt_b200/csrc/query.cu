@@ -690,14 +690,7 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     if (dp_env) {
         device_pack = atoi(dp_env) != 0 && can_device_pack;
     } else if (can_device_pack) {
-        const int rule = Pool::get().size() < 4 ? 1 : 0;
-        const double *rate = idx->pack_rate;
-        int best = rule;
-        if (rate[0] > 0 && rate[1] > 0) best = rate[1] > 1.05 * rate[0] ? 1 : (rate[0] > 1.05 * rate[1] ? 0 : rule);
-        if (!large_call) device_pack = best != 0;
-        else if (rate[rule] == 0) device_pack = rule != 0;
-        else if (rate[1 - rule] == 0) device_pack = rule == 0;
-        else device_pack = (idx->large_calls % 64 == 63) ? best == 0 : best != 0;
+        device_pack = choose_device_pack(Pool::get().size() < 4 ? 1 : 0, idx->pack_rate, large_call, idx->large_calls);   // tasks.h
     }
     idx->last_packing = device_pack ? 1 : 0;
 

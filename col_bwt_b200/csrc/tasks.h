@@ -34,6 +34,20 @@ struct SplitParams {
     }
 };
 
+// Where colbwt_query packs the reads of a call that could go either way (pinned input, short reads).  rate[0] / rate[1] =
+// bases/s of the last large call packed on the host / on the device (0 = not measured yet); `rule` = the starting guess.
+// Large calls: measure the rule first, then the other way once, then keep the faster (5 % hysteresis, ties -> rule) and
+// try the other one again on every 64th large call.  Small calls follow what the large ones found.
+inline bool choose_device_pack(int rule, const double rate[2], bool large_call, uint32_t large_calls)
+{
+    int best = rule;
+    if (rate[0] > 0 && rate[1] > 0) best = rate[1] > 1.05 * rate[0] ? 1 : (rate[0] > 1.05 * rate[1] ? 0 : rule);
+    if (!large_call) return best != 0;
+    if (rate[rule] == 0) return rule != 0;
+    if (rate[1 - rule] == 0) return rule == 0;
+    return (large_calls % 64 == 63) ? best == 0 : best != 0;
+}
+
 struct TaskPlan {
     std::vector<ChunkTask> tasks;     // scheduling order: packed tasks (longest first), then byte tasks (longest first)
     std::vector<ChunkTask> by_slot;   // slot order

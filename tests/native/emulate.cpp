@@ -214,6 +214,11 @@ uint32_t emu_plan(uint32_t len, uint32_t chunk, uint32_t warm, uint32_t *out, ui
     return (uint32_t)plan.by_slot.size();
 }
 
+int emu_choose_device_pack(int rule, double rate_host, double rate_device, int large_call, uint32_t large_calls)
+{
+    const double rate[2] = {rate_host, rate_device};
+    return choose_device_pack(rule, rate, large_call != 0, large_calls) ? 1 : 0;
+}
 int emu_pack(const uint8_t *seq, uint64_t len, uint32_t *words) { return pack_read_2bit(seq, len, words) ? 1 : 0; }
 uint64_t emu_slow_rows(EmuTable *t) { return t->slow_rows; }
 uint32_t emu_flags(EmuTable *t) { return t->flags; }

@@ -245,3 +245,23 @@ def test_chunk_planner_tiles_the_read(length, chunk, warm):
     assert (t[:, 1] > t[:, 0]).all() and (t[:, 1] - t[:, 0]).max() - (t[:, 1] - t[:, 0]).min() <= n
     assert (t[1:, 2] == np.minimum(length, t[1:, 1] + warm)).all()
     assert (t[:, 3] == np.arange(n)).all()
+
+
+def test_packing_choice_is_measured_then_kept():
+    """tasks.h: choose_device_pack -- the rule first, the other way once, then the faster one with hysteresis."""
+    import ctypes as C
+    from emu import build, SO
+    build()
+    L = C.CDLL(SO)
+    L.emu_choose_device_pack.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint32]
+    f = lambda rule, h, d, large=1, calls=0: bool(L.emu_choose_device_pack(rule, h, d, large, calls))
+    for rule in (0, 1):
+        assert f(rule, 0, 0) == bool(rule)                   # nothing measured: the rule
+        assert f(rule, 0, 0, large=0) == bool(rule)
+        host_known, dev_known = (20e9, 0) if rule == 0 else (0, 17e9)
+        assert f(rule, host_known, dev_known) == (not rule)  # the rule was measured: try the other way once
+        assert f(rule, host_known, dev_known, large=0) == bool(rule)   # small calls never probe
+        assert f(rule, 20e9, 17e9) is False and f(rule, 6e9, 12e9) is True
+        assert f(rule, 20e9, 20.5e9) == bool(rule)           # within 5 %: stay with the rule
+        assert f(rule, 20e9, 17e9, calls=63) is True and f(rule, 6e9, 12e9, calls=127) is False   # periodic re-try
+        assert f(rule, 20e9, 17e9, large=0, calls=63) is False
