@@ -420,6 +420,10 @@ def main():
         b, t = run(kk)
         cpu = {"value": b / t, "unit": "bases/s", "cores": threads, "kind": kind,
                "sample": f"first {kk} reads ({b} bases) of the same batch, {t:.2f} s; MULTI_THREAD off (output-identical, SURVEY.md 6)"}
+        if threads > 1:   # the same harness on one core, a ~2 s sample
+            k1, run1 = time_cpu(ref, kind, seqs, off, 1, min(2.0, a.cpu_seconds))
+            b1, t1 = run1(k1)
+            cpu["one_core"] = {"value": b1 / t1, "unit": "bases/s", "sample": f"first {k1} reads ({b1} bases), {t1:.2f} s"}
 
     out = {
         "metric": "query bases/sec (PML + chain stats)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": a.steps,
