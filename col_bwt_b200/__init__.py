@@ -54,6 +54,10 @@ EXPORTS = {
     "colbwt_index_free": (None, [C.c_void_p]),
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
     "colbwt_index_last_packing": (C.c_int, [C.c_void_p]),
+    "colbwt_index_last_transport": (C.c_int, [C.c_void_p]),
+    "colbwt_compact_bound": (C.c_size_t, [C.c_void_p, C.c_uint64]),
+    "colbwt_query_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "colbwt_compact_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
     "colbwt_host_alloc": (C.c_void_p, [C.c_size_t]),
     "colbwt_host_free": (None, [C.c_void_p]),
     "colbwt_batch_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
@@ -229,6 +233,23 @@ class ColPml:
                                cid.ctypes.data), "colbwt_query")
         return pml, cid
 
+    def query_compact(self, seqs, offsets, out: np.ndarray | None = None, capacity: int | None = None):
+        """Same traversal, compact result (one match bit per base + the non-zero chain ids; include/colbwt_b200.h).
+        Returns the used part of the result buffer (uint8 view); `out` = caller (e.g. pinned) uint8 buffer."""
+        seqs, offsets = _as_batch(seqs, offsets)
+        if out is None:
+            cap = capacity or int(_L.colbwt_compact_bound(offsets.ctypes.data, offsets.size - 1))
+            out = np.empty(max(cap, 64), np.uint8)
+        used = C.c_size_t()
+        _check(_L.colbwt_query_compact(self._h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, out.ctypes.data, out.size,
+                                       C.byref(used)), "colbwt_query_compact")
+        return out[: used.value]
+
+    @property
+    def last_transport(self) -> str:
+        """How the dense results of the last query() crossed the link: "dense" or "compact" (expanded on the host)."""
+        return "compact" if _L.colbwt_index_last_transport(self._h) == 1 else "dense"
+
     @property
     def last_packing(self) -> str:
         """Where the last query() packed the reads: "host" or "device" (the library measures both and keeps the faster)."""
@@ -252,6 +273,29 @@ class ColPml:
             self._h = None
 
     __del__ = close
+
+
+def compact_expand(result: np.ndarray, offsets, pml_width: int = PML_U16):
+    """Dense (pml, cid) arrays from a compact result -- host only, no GPU needed."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    result = np.ascontiguousarray(result, dtype=np.uint8)
+    total = int(offsets[-1] - offsets[0])
+    pml = np.empty(total, _PML_DTYPE[pml_width])
+    cid = np.empty(total, np.uint8)
+    _check(_L.colbwt_compact_expand(result.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data, pml_width, cid.ctypes.data),
+           "colbwt_compact_expand")
+    return pml, cid
+
+
+def compact_segments(result: np.ndarray):
+    """The directory of a compact result as a list of dicts (offsets in bytes into `result`)."""
+    hdr = np.frombuffer(result[:64].tobytes(), "<u8")
+    if hdr[0] != 0x31504d4354574243:
+        raise ValueError("not a compact result")
+    n = int(hdr[1])
+    d = np.frombuffer(result[64: 64 + 72 * n].tobytes(), "<u8").reshape(n, 9)
+    keys = ("first_read", "n_reads", "first_base", "n_bases", "match_off", "cid_off", "prefix_off", "values_off", "n_values")
+    return [dict(zip(keys, map(int, row))) for row in d]
 
 
 def col_split(prefix: str, mode: str = "tunnels", split_rate: int = 10, device: int = 0):

@@ -25,6 +25,22 @@ void set_error(const char *fmt, ...);
         }                                                                                               \
     } while (0)
 
+// Compact result form of one chunk (compact.cu / expand.cpp): match words | chain-id words | prefix, then the values.
+constexpr uint32_t COMPACT_GROUP_WORDS = 64;   // one prefix entry per 64 words = 2048 bases
+struct CompactLayout {
+    uint64_t n_words, n_groups, match_off, cid_off, prefix_off, fixed_bytes;
+    explicit CompactLayout(uint64_t n_bases)
+    {
+        n_words = (n_bases + 31) / 32;
+        n_groups = (n_words + COMPACT_GROUP_WORDS - 1) / COMPACT_GROUP_WORDS;
+        const uint64_t wb = (n_words * 4 + 15) & ~15ull;
+        match_off = 0;
+        cid_off = wb;
+        prefix_off = 2 * wb;
+        fixed_bytes = prefix_off + (((n_groups + 1) * 4 + 15) & ~15ull);
+    }
+};
+
 // The table in the HBM of one GPU.
 struct DeviceTable {
     int device = -1;
@@ -45,11 +61,10 @@ struct colbwt_index {
     uint8_t code_lut[256];
     std::mutex query_mutex;                 // one colbwt_query at a time per index
     colbwt::Pipeline *pipeline = nullptr;   // staging buffers + streams, kept between colbwt_query calls
-    // Where colbwt_query packs the reads (query.cu): bases/s of the last large call packed on the host [0] / on the device [1],
-    // the number of large calls so far, and what the last call did.
-    double pack_rate[2] = {0.0, 0.0};
-    uint32_t large_calls = 0;
-    int last_packing = 0;
+    // How colbwt_query [0] / colbwt_query_compact [1] ran (query.cu): bases/s of the last large call in each mode (bit 0:
+    // reads packed on the device, bit 1: compact transport of dense results; 0 = not measured yet), and what the last call did.
+    double mode_rate[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    int last_packing = 0, last_transport = 0;
 };
 
 namespace colbwt {
@@ -81,6 +96,15 @@ bool pack_read_2bit(const uint8_t *seq, uint64_t len, uint32_t *words);
 // seq_end = number of readable bytes in seqs (bounds the 32-byte over-reads); irregular read numbers go to irr.
 void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t r_base, uint64_t base0,
                 uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr);
+
+// compact.cu: dense PML/CID of one chunk (still in HBM) -> compact form.  d_out holds CompactLayout(n_bases).fixed_bytes,
+// d_group_count n_groups + 1 words, d_values up to n_bases bytes.
+size_t compact_scan_temp_bytes(uint64_t max_groups);
+int launch_compact(const void *d_pml, int pml_width, const uint8_t *d_cid, uint64_t n_bases, uint8_t *d_out, uint32_t *d_group_count,
+                   void *d_scan_temp, size_t scan_temp_bytes, uint8_t *d_values, cudaStream_t stream);
+// expand.cpp: reads [ra, rb) of the segment starting at read r_first, back to dense arrays (pml / cid point at the segment's base 0).
+void expand_reads(const uint32_t *match, const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, const uint64_t *off,
+                  uint64_t r_first, uint64_t ra, uint64_t rb, void *pml, int pml_width, uint8_t *cid);
 
 // Kernels launched through host wrappers (traverse.cu).
 // Device-side packing of a chunk's raw bytes (traverse.cu: k_pack_reads).

@@ -32,12 +32,16 @@ public:
         return p;
     }
     int size() const { return (int)workers_.size() + 1; }
+    // One job at a time: the job lives in shared fields (fn_, n_tasks_, next_, pending_, epoch_), and the pool is shared by
+    // every index and every calling thread of the process (colbwt_query on two indexes, colbwt_batch_upload next to a query,
+    // the per-device feeder threads), so callers queue on caller_m_ for the whole parallel_for.
     void parallel_for(int n_tasks, const std::function<void(int)> &fn)
     {
         if (n_tasks <= 1 || workers_.empty()) {
             for (int i = 0; i < n_tasks; ++i) fn(i);
             return;
         }
+        std::lock_guard<std::mutex> one_job(caller_m_);
         {
             std::lock_guard<std::mutex> g(m_);
             fn_ = &fn;
@@ -98,6 +102,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
+    std::mutex caller_m_;   // serialises parallel_for callers
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)> *fn_ = nullptr;
@@ -484,30 +489,43 @@ namespace colbwt {
 // leaves the D2H copy engine (the end-to-end bottleneck: 2-3 bytes out per base over PCIe) idle between chunks.
 static const int SLOTS_PER_DEVICE = getenv("COLBWT_SLOTS") ? std::max(1, std::min(16, atoi(getenv("COLBWT_SLOTS")))) : 6;
 
+// What a call hands back, and how the results cross the link.
+enum OutKind {
+    OUT_DENSE = 0,              // dense PML + CID arrays, copied as they are (2-5 bytes per base over PCIe)
+    OUT_DENSE_VIA_COMPACT = 1,  // dense arrays for the caller, but the link carries the compact form and the host threads expand it
+    OUT_COMPACT = 2             // colbwt_query_compact: the compact form is the result
+};
+
 struct Slot {
     // pinned host staging
     ReadMeta *h_meta = nullptr, *h_meta_b = nullptr;
     uint32_t *h_words = nullptr;
-    uint8_t *h_bytes = nullptr, *h_out = nullptr;
+    uint8_t *h_bytes = nullptr, *h_out = nullptr;   // h_out: dense results (pageable destination) or the compact form
     // device
     ReadMeta *d_meta = nullptr, *d_meta_b = nullptr;
     uint32_t *d_words = nullptr;
     uint8_t *d_bytes = nullptr, *d_pml = nullptr, *d_cid = nullptr;
+    uint8_t *d_compact = nullptr, *d_values = nullptr;   // compact form of the chunk: fixed part, non-zero chain ids
+    uint32_t *d_group_count = nullptr;
+    void *d_scan_temp = nullptr;
     unsigned long long *d_cursors = nullptr;
     DevicePlan plan;
     cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, fixed_done = nullptr;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};   // COLBWT_TRACE=2: H2D start / kernel start / D2H start / end
-    // pending copy-out when the caller's buffers are not pinned
+    // the chunk in flight
     bool pending = false;
-    uint64_t out_base = 0, out_bases = 0;
+    int phase = 0;              // compact forms: 1 = fixed part on its way, values not yet requested; 2 = everything enqueued
+    size_t chunk = 0;           // index into the job's chunk list
+    uint64_t out_base = 0, out_bases = 0, n_values = 0, values_off = 0;
 };
 
 struct Pipeline {
     colbwt_index *idx = nullptr;
-    uint64_t cap_reads = 0, cap_bases = 0;
+    uint64_t cap_reads = 0, cap_bases = 0, h_out_bytes = 0, compact_fixed_cap = 0;
+    size_t scan_temp_bytes = 0;
     int pml_width = 0;
-    bool staged_out = false;
+    bool staged_out = false, compact = false;
     std::vector<Slot> slots;   // n_devices * SLOTS_PER_DEVICE
     ~Pipeline()
     {
@@ -525,9 +543,14 @@ struct Pipeline {
             cudaFree(k.d_bytes);
             cudaFree(k.d_pml);
             cudaFree(k.d_cid);
+            cudaFree(k.d_compact);
+            cudaFree(k.d_values);
+            cudaFree(k.d_group_count);
+            cudaFree(k.d_scan_temp);
             cudaFree(k.d_cursors);
             k.plan.release();
             if (k.done) cudaEventDestroy(k.done);
+            if (k.fixed_done) cudaEventDestroy(k.fixed_done);
             for (auto e : k.tev) if (e) cudaEventDestroy(e);
             if (k.stream) cudaStreamDestroy(k.stream);
         }
@@ -546,13 +569,22 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-// Allocate (or reuse) the staging pipeline of an index.
-static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_bases, int pml_width, bool staged_out, Pipeline **out)
+// Allocate (or reuse) the staging pipeline of an index.  A pipeline that is replaced hands its features on (staged dense
+// output, compact buffers), so that alternating kinds of calls do not reallocate every time.
+static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_bases, int pml_width, bool staged_out, bool compact, Pipeline **out)
 {
     Pipeline *p = idx->pipeline;
-    if (p && p->cap_reads >= chunk_reads && p->cap_bases >= chunk_bases && p->pml_width >= pml_width && (p->staged_out || !staged_out)) {
+    if (p && p->cap_reads >= chunk_reads && p->cap_bases >= chunk_bases && p->pml_width >= pml_width && (p->staged_out || !staged_out) &&
+        (p->compact || !compact)) {
         *out = p;
         return COLBWT_OK;
+    }
+    if (p) {
+        chunk_reads = std::max(chunk_reads, p->cap_reads);
+        chunk_bases = std::max(chunk_bases, p->cap_bases);
+        pml_width = std::max(pml_width, p->pml_width);
+        staged_out |= p->staged_out;
+        compact |= p->compact;
     }
     delete p;
     idx->pipeline = nullptr;
@@ -562,9 +594,14 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
     pl->cap_bases = chunk_bases;
     pl->pml_width = pml_width;
     pl->staged_out = staged_out;
+    pl->compact = compact;
     pl->slots.resize(idx->dev.size() * SLOTS_PER_DEVICE);
     const uint64_t cap_words = chunk_bases / 16 + chunk_reads + 2;
-    const uint64_t out_bytes = chunk_bases * (uint64_t)(pml_width + 1) + 64;
+    const CompactLayout lay(chunk_bases);
+    pl->compact_fixed_cap = lay.fixed_bytes;
+    pl->scan_temp_bytes = compact ? compact_scan_temp_bytes(lay.n_groups + 1) : 0;
+    pl->h_out_bytes = std::max<uint64_t>(staged_out ? chunk_bases * (uint64_t)(pml_width + 1) + 64 : 0,
+                                         compact ? lay.fixed_bytes + chunk_bases + 64 : 0);
     for (size_t s = 0; s < pl->slots.size(); ++s) {
         CB_CUDA(cudaSetDevice(idx->dev[s / SLOTS_PER_DEVICE].device));
         Slot &k = pl->slots[s];
@@ -572,16 +609,23 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
         CB_CUDA(cudaMallocHost(&k.h_meta_b, chunk_reads * sizeof(ReadMeta)));
         CB_CUDA(cudaMallocHost(&k.h_words, cap_words * 4));
         CB_CUDA(cudaMallocHost(&k.h_bytes, chunk_bases + 16));
-        if (staged_out) CB_CUDA(cudaMallocHost(&k.h_out, out_bytes));
+        if (pl->h_out_bytes) CB_CUDA(cudaMallocHost(&k.h_out, pl->h_out_bytes));
         CB_CUDA(cudaMalloc(&k.d_meta, chunk_reads * sizeof(ReadMeta)));
         CB_CUDA(cudaMalloc(&k.d_meta_b, chunk_reads * sizeof(ReadMeta)));
         CB_CUDA(cudaMalloc(&k.d_words, cap_words * 4));
         CB_CUDA(cudaMalloc(&k.d_bytes, chunk_bases + 16));
         CB_CUDA(cudaMalloc(&k.d_pml, (chunk_bases + 8) * (uint64_t)pml_width));
         CB_CUDA(cudaMalloc(&k.d_cid, chunk_bases + 8));
+        if (compact) {
+            CB_CUDA(cudaMalloc(&k.d_compact, lay.fixed_bytes));
+            CB_CUDA(cudaMalloc(&k.d_values, chunk_bases + 16));
+            CB_CUDA(cudaMalloc(&k.d_group_count, (lay.n_groups + 2) * sizeof(uint32_t)));
+            CB_CUDA(cudaMalloc(&k.d_scan_temp, std::max<size_t>(pl->scan_temp_bytes, 16)));
+        }
         CB_CUDA(cudaMalloc(&k.d_cursors, 4 * sizeof(unsigned long long)));
         CB_CUDA(cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking));
         CB_CUDA(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&k.fixed_done, cudaEventDisableTiming));
         for (auto &e : k.tev) CB_CUDA(cudaEventCreate(&e));
     }
     idx->pipeline = pl.release();
@@ -589,17 +633,503 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
     return COLBWT_OK;
 }
 
-} // namespace colbwt
+// ---- chunk planning -------------------------------------------------------------------------------------------
+struct Chunk { uint64_t r0, r1; };
+struct Geometry { uint64_t chunk_bases = 0, chunk_reads = 0; uint32_t max_len = 0; };
 
-static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid);
-
-extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
-                            void *pml, int pml_width, uint8_t *cid)
+// One pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB.
+static int scan_offsets(const uint64_t *off, uint64_t n_reads, uint32_t *max_len_out)
 {
-    const int rc = query_impl(idx, seqs, off, n_reads, pml, pml_width, cid);
-    if (rc != COLBWT_OK && rc != COLBWT_ERR_ARG && idx && idx->pipeline) {
+    const int T = n_reads >= (1u << 16) ? Pool::get().size() : 1;
+    std::vector<uint64_t> part_max((size_t)T, 0), part_bad((size_t)T, UINT64_MAX);
+    Pool::get().parallel_for(T, [&](int t) {
+        const uint64_t a = n_reads * (uint64_t)t / (uint64_t)T, b = n_reads * (uint64_t)(t + 1) / (uint64_t)T;
+        uint64_t mx = 0, bad = UINT64_MAX;
+        for (uint64_t i = a; i < b; ++i) {
+            if (off[i + 1] < off[i]) bad = std::min(bad, i);
+            else mx = std::max(mx, off[i + 1] - off[i]);
+        }
+        part_max[(size_t)t] = mx;
+        part_bad[(size_t)t] = bad;
+    });
+    const uint64_t bad = *std::min_element(part_bad.begin(), part_bad.end());
+    if (bad != UINT64_MAX) {
+        set_error("colbwt_query: offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
+        return COLBWT_ERR_ARG;
+    }
+    const uint64_t mx = *std::max_element(part_max.begin(), part_max.end());
+    if (mx >= 0xFFFFFFFFull) {
+        set_error("a read of 2^32-1 or more bases is not supported");
+        return COLBWT_ERR_ARG;
+    }
+    *max_len_out = (uint32_t)mx;
+    return COLBWT_OK;
+}
+
+// staged_bytes_per_base: bytes of pinned staging a base of output needs when the destination cannot be DMA-ed into
+// directly (0 otherwise); bounds the chunk so that one slot's staging stays under 256 MB.
+static Geometry chunk_geometry(uint64_t total_bases, uint64_t n_reads, uint32_t max_len, uint64_t staged_bytes_per_base)
+{
+    Geometry g;
+    g.max_len = max_len;
+    uint64_t chunk_bases = 96ull << 20;   // measured on C2 (profiles/r1/e2e_chunk_sweep.log): 16/24/32/48/96/128/192 M -> 83.6/85.0/81.1/76.3/71.8-73.2/72.0/73.1 ms
+    const char *env = getenv("COLBWT_CHUNK_BASES");
+    if (env) chunk_bases = std::max<uint64_t>(1024, strtoull(env, nullptr, 10));
+    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read at a time and
+    // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
+    if (!env) chunk_bases = std::max<uint64_t>(chunk_bases, std::min<uint64_t>(512ull << 20, (total_bases / std::max<uint64_t>(1, n_reads)) * 32768));
+    if (staged_bytes_per_base && !env) chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / staged_bytes_per_base);
+    chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
+    chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
+    g.chunk_bases = chunk_bases;
+    // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
+    g.chunk_reads = std::min<uint64_t>(std::max<uint64_t>(chunk_bases / 32, 1024), n_reads);
+    return g;
+}
+
+static void plan_chunks(const uint64_t *off, uint64_t n_reads, const Geometry &g, std::vector<Chunk> &chunks)
+{
+    chunks.clear();
+    for (uint64_t r0 = 0; r0 < n_reads;) {   // at most chunk_bases bases and chunk_reads reads, at least one read
+        uint64_t r1 = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + g.chunk_bases) - off) - 1;
+        r1 = std::min(r1, r0 + g.chunk_reads);
+        if (r1 <= r0) r1 = r0 + 1;
+        chunks.push_back(Chunk{r0, r1});
+        r0 = r1;
+    }
+}
+
+// ---- one call ---------------------------------------------------------------------------------------------------
+struct QueryJob {
+    colbwt_index *idx = nullptr;
+    Pipeline *pl = nullptr;
+    const uint8_t *seqs = nullptr;
+    const uint64_t *off = nullptr;
+    uint64_t n_reads = 0;
+    int pml_width = 0;
+    OutKind kind = OUT_DENSE;
+    bool device_pack = false, staged_out = false;
+    uint8_t *pml = nullptr, *cid = nullptr;                // dense destination
+    uint8_t *cbuf = nullptr;                               // compact destination (colbwt_query_compact)
+    size_t ccap = 0;
+    bool cbuf_pinned = false;
+    colbwt_compact_segment *segments = nullptr;            // directory inside cbuf
+    std::atomic<uint64_t> values_cursor{0};                // bump allocator for the value regions inside cbuf
+    std::vector<Chunk> chunks;
+    std::atomic<size_t> next_chunk{0};
+    std::atomic<int> rc{COLBWT_OK};
+    std::mutex err_m;
+    std::string err;
+    int trace = 0;
+    cudaEvent_t origin = nullptr;                          // COLBWT_TRACE=2, single device: timeline origin
+    struct ChunkTimes { float h2d0, k0, d2h0, end; };
+    std::vector<ChunkTimes> timeline;
+    struct DevTimes { double pack = 0, wait = 0, enqueue = 0, post = 0, loop = 0; uint64_t chunks = 0; };
+    std::vector<DevTimes> times;
+
+    void fail(int code)
+    {
+        std::lock_guard<std::mutex> g(err_m);
+        if (rc.load() == COLBWT_OK) {
+            err = colbwt_last_error();
+            rc.store(code);
+        }
+    }
+};
+
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Split reads [r0, r1) into T slices of about equal bases; slice t = [cut[t], cut[t+1]).
+static std::vector<uint64_t> slice_reads(const uint64_t *off, uint64_t r0, uint64_t r1, int T)
+{
+    std::vector<uint64_t> cut((size_t)T + 1);
+    const uint64_t b0 = off[r0], nb = off[r1] - b0;
+    for (int t = 0; t <= T; ++t) cut[(size_t)t] = (t == T) ? r1 : (uint64_t)(std::lower_bound(off + r0, off + r1, b0 + nb * (uint64_t)t / (uint64_t)T) - off);
+    cut[0] = r0;
+    return cut;
+}
+
+// Compact forms, second phase: the fixed part (bit words + prefix) has arrived, so the number of non-zero chain ids is
+// known: request exactly those bytes.
+static int finish_values(QueryJob &J, Slot &k)
+{
+    if (k.phase != 1) return COLBWT_OK;
+    CB_CUDA(cudaEventSynchronize(k.fixed_done));
+    const CompactLayout lay(k.out_bases);
+    const bool direct = J.kind == OUT_COMPACT && J.cbuf_pinned;
+    const uint8_t *fixed = direct ? J.cbuf + J.segments[k.chunk].match_off : k.h_out;
+    k.n_values = reinterpret_cast<const uint32_t *>(fixed + lay.prefix_off)[lay.n_groups];
+    uint8_t *dst = k.h_out + J.pl->compact_fixed_cap;
+    if (J.kind == OUT_COMPACT) {
+        k.values_off = J.values_cursor.fetch_add((k.n_values + 15) & ~15ull);
+        if (k.values_off + k.n_values > J.ccap) {
+            set_error("colbwt_query_compact: result buffer of %zu bytes is too small (more than %llu needed; colbwt_compact_bound gives the worst case)",
+                      J.ccap, (unsigned long long)(k.values_off + k.n_values));
+            return COLBWT_ERR_NOMEM;
+        }
+        if (direct) dst = J.cbuf + k.values_off;
+    }
+    if (k.n_values) CB_CUDA(cudaMemcpyAsync(dst, k.d_values, k.n_values, cudaMemcpyDeviceToHost, k.stream));
+    if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
+    CB_CUDA(cudaEventRecord(k.done, k.stream));
+    k.phase = 2;
+    return COLBWT_OK;
+}
+
+// Wait for the slot's chunk and finish it on the host: copy out of / expand from the staging area, fill the directory.
+static int drain(QueryJob &J, Slot &k, QueryJob::DevTimes &tm)
+{
+    if (!k.pending) return COLBWT_OK;
+    double t0 = now_s();
+    if (int rc = finish_values(J, k)) return rc;
+    CB_CUDA(cudaEventSynchronize(k.done));
+    tm.wait += now_s() - t0;
+    if (J.trace >= 2 && J.origin) {
+        QueryJob::ChunkTimes ct{};
+        cudaEventElapsedTime(&ct.h2d0, J.origin, k.tev[0]);
+        cudaEventElapsedTime(&ct.k0, J.origin, k.tev[1]);
+        cudaEventElapsedTime(&ct.d2h0, J.origin, k.tev[2]);
+        cudaEventElapsedTime(&ct.end, J.origin, k.tev[3]);
+        J.timeline.push_back(ct);
+    }
+    t0 = now_s();
+    const Chunk &c = J.chunks[k.chunk];
+    Pool &pool = Pool::get();
+    if (J.kind == OUT_DENSE) {
+        if (J.staged_out) {   // pageable destination: copy out with all packing threads (first-touch page faults included)
+            uint8_t *dst[2] = {J.pml + k.out_base * (uint64_t)J.pml_width, J.cid + k.out_base};
+            const uint8_t *src[2] = {k.h_out, k.h_out + J.pl->cap_bases * (uint64_t)J.pml_width + 32};
+            const uint64_t bytes[2] = {k.out_bases * (uint64_t)J.pml_width, k.out_bases};
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size(), (bytes[0] + bytes[1]) >> 20));
+            pool.parallel_for(2 * T, [&](int i) {
+                const int a = i / T, t = i % T;
+                const uint64_t lo = bytes[a] * (uint64_t)t / (uint64_t)T, hi = bytes[a] * (uint64_t)(t + 1) / (uint64_t)T;
+                memcpy(dst[a] + lo, src[a] + lo, hi - lo);
+            });
+        }
+    } else if (k.out_bases) {
+        const CompactLayout lay(k.out_bases);
+        if (J.kind == OUT_DENSE_VIA_COMPACT) {
+            const uint8_t *fx = k.h_out, *vals = k.h_out + J.pl->compact_fixed_cap;
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, k.out_bases >> 16));
+            const std::vector<uint64_t> cut = slice_reads(J.off, c.r0, c.r1, T);
+            pool.parallel_for(T, [&](int t) {
+                expand_reads(reinterpret_cast<const uint32_t *>(fx + lay.match_off), reinterpret_cast<const uint32_t *>(fx + lay.cid_off),
+                             reinterpret_cast<const uint32_t *>(fx + lay.prefix_off), vals, J.off, c.r0, cut[(size_t)t], cut[(size_t)t + 1],
+                             J.pml + k.out_base * (uint64_t)J.pml_width, J.pml_width, J.cid + k.out_base);
+            });
+        } else {
+            colbwt_compact_segment &sg = J.segments[k.chunk];
+            sg.values_off = k.values_off;
+            sg.n_values = k.n_values;
+            if (!J.cbuf_pinned) {
+                memcpy(J.cbuf + sg.match_off, k.h_out, lay.fixed_bytes);
+                memcpy(J.cbuf + sg.values_off, k.h_out + J.pl->compact_fixed_cap, k.n_values);
+            }
+        }
+    }
+    k.pending = false;
+    k.phase = 0;
+    tm.post += now_s() - t0;
+    return COLBWT_OK;
+}
+
+// Pack chunk c into the slot's staging and enqueue its H2D -> traversal -> D2H chain on the slot's stream.
+static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTimes &tm)
+{
+    Pipeline &pl = *J.pl;
+    const DeviceTable &dt = J.idx->dev[(size_t)d];
+    const Chunk &c = J.chunks[ci];
+    const uint64_t *off = J.off;
+    double t0 = now_s();
+    Staging st;
+    st.meta = k.h_meta;
+    st.meta_b = k.h_meta_b;
+    st.words = k.h_words;
+    st.bytes = k.h_bytes;
+    if (J.device_pack) prepare_offsets_only(off, c.r0, c.r1, st);
+    else prepare_reads(J.seqs, off, c.r0, c.r1, off[J.n_reads], (uint64_t)dt.sm_count * 1024 / (uint64_t)std::min<int>(SLOTS_PER_DEVICE, 4), st);
+    tm.pack += now_s() - t0;
+    t0 = now_s();
+
+    if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[0], k.stream));
+    CB_CUDA(cudaMemcpyAsync(k.d_meta, k.h_meta, st.n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
+    if (J.device_pack) {
+        CB_CUDA(cudaMemcpyAsync(k.d_bytes, J.seqs + off[c.r0], st.n_bases, cudaMemcpyHostToDevice, k.stream));
+        if (int rc = launch_pack(dt, k.d_bytes, k.d_meta, (uint32_t)st.n_reads, k.d_words, k.d_meta_b, (uint32_t *)(k.d_cursors + 3), k.stream)) return rc;
+    } else {
+        CB_CUDA(cudaMemcpyAsync(k.d_words, k.h_words, st.n_words * 4, cudaMemcpyHostToDevice, k.stream));
+        if (st.n_irregular) {
+            CB_CUDA(cudaMemcpyAsync(k.d_meta_b, k.h_meta_b, st.n_irregular * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
+            CB_CUDA(cudaMemcpyAsync(k.d_bytes, k.h_bytes, st.n_byte_bases, cudaMemcpyHostToDevice, k.stream));
+        }
+    }
+    BatchView bv{};
+    bv.meta = k.d_meta;
+    bv.meta_b = k.d_meta_b;
+    bv.words = k.d_words;
+    bv.bytes = k.d_bytes;
+    bv.pml = k.d_pml;
+    bv.cid = k.d_cid;
+    bv.n_packed = (uint32_t)st.n_reads;
+    bv.n_bytes = (uint32_t)st.n_irregular;
+    bv.n_bytes_dev = J.device_pack ? (const uint32_t *)(k.d_cursors + 3) : nullptr;
+    if (int rc = upload_plan(st.plan, k.plan, bv, k.stream)) return rc;
+    if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[1], k.stream));
+    if (int rc = launch_traverse(dt, bv, J.pml_width, k.d_cursors, k.stream)) return rc;
+    const uint64_t ob = off[c.r0] - off[0];
+    k.chunk = ci;
+    k.out_base = ob;
+    k.out_bases = st.n_bases;
+    k.n_values = 0;
+    k.values_off = 0;
+    k.phase = 2;
+    if (J.kind == OUT_DENSE) {
+        if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
+        if (J.staged_out) {
+            CB_CUDA(cudaMemcpyAsync(k.h_out, k.d_pml, st.n_bases * (uint64_t)J.pml_width, cudaMemcpyDeviceToHost, k.stream));
+            CB_CUDA(cudaMemcpyAsync(k.h_out + pl.cap_bases * (uint64_t)J.pml_width + 32, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
+        } else {
+            CB_CUDA(cudaMemcpyAsync(J.pml + ob * (uint64_t)J.pml_width, k.d_pml, st.n_bases * (uint64_t)J.pml_width, cudaMemcpyDeviceToHost, k.stream));
+            CB_CUDA(cudaMemcpyAsync(J.cid + ob, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
+        }
+        if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
+        CB_CUDA(cudaEventRecord(k.done, k.stream));
+    } else if (st.n_bases) {
+        // dense results stay in HBM; the link carries the compact form (compact.cu) in two steps: the fixed-size part
+        // now, the non-zero chain ids once their number is known (finish_values)
+        const CompactLayout lay(st.n_bases);
+        if (int rc = launch_compact(k.d_pml, J.pml_width, k.d_cid, st.n_bases, k.d_compact, k.d_group_count, k.d_scan_temp, pl.scan_temp_bytes, k.d_values, k.stream)) return rc;
+        if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
+        uint8_t *dst = (J.kind == OUT_COMPACT && J.cbuf_pinned) ? J.cbuf + J.segments[ci].match_off : k.h_out;
+        CB_CUDA(cudaMemcpyAsync(dst, k.d_compact, lay.fixed_bytes, cudaMemcpyDeviceToHost, k.stream));
+        CB_CUDA(cudaEventRecord(k.fixed_done, k.stream));
+        k.phase = 1;
+    } else {
+        if (J.trace >= 2) {
+            CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
+            CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
+        }
+        CB_CUDA(cudaEventRecord(k.done, k.stream));
+    }
+    k.pending = true;
+    tm.enqueue += now_s() - t0;
+    return COLBWT_OK;
+}
+
+// The feeder of one device: takes the next unassigned chunk, waits for a free slot, packs, enqueues.  With several
+// replicas each device has its own feeder thread (reads are independent: src/pml_query.cpp:74-86), so a device never
+// waits for another one's drain; the packing threads are shared (Pool).
+static void feed_device(QueryJob &J, int d)
+{
+    QueryJob::DevTimes &tm = J.times[(size_t)d];
+    const double t_begin = now_s();
+    if (cudaSetDevice(J.idx->dev[(size_t)d].device) != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed", J.idx->dev[(size_t)d].device);
+        J.fail(COLBWT_ERR_CUDA);
+        return;
+    }
+    Slot *slots = &J.pl->slots[(size_t)d * SLOTS_PER_DEVICE];
+    Slot *prev = nullptr;
+    int rc = COLBWT_OK;
+    for (uint64_t local = 0; rc == COLBWT_OK && J.rc.load() == COLBWT_OK; ++local) {
+        const size_t ci = J.next_chunk.fetch_add(1);
+        if (ci >= J.chunks.size()) break;
+        Slot &k = slots[local % (uint64_t)SLOTS_PER_DEVICE];
+        if ((rc = drain(J, k, tm)) != COLBWT_OK) break;
+        if ((rc = enqueue_chunk(J, d, k, ci, tm)) != COLBWT_OK) break;
+        if (prev && prev != &k) rc = finish_values(J, *prev);   // one chunk behind: the GPU always has the next one queued
+        prev = &k;
+        ++tm.chunks;
+    }
+    tm.loop = now_s() - t_begin;
+    for (int s = 0; s < SLOTS_PER_DEVICE && rc == COLBWT_OK; ++s) rc = drain(J, slots[s], tm);
+    if (rc != COLBWT_OK) J.fail(rc);
+}
+
+struct CallSpec {
+    OutKind kind = OUT_DENSE;              // OUT_DENSE: the library may still pick OUT_DENSE_VIA_COMPACT
+    void *pml = nullptr;
+    int pml_width = 0;
+    uint8_t *cid = nullptr;
+    void *cbuf = nullptr;
+    size_t ccap = 0;
+    size_t *cused = nullptr;
+};
+
+static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, const CallSpec &cs)
+{
+    const bool compact_api = cs.kind == OUT_COMPACT;
+    const uint64_t total_bases = off[n_reads] - off[0];
+    uint32_t max_len = 0;
+    if (int rc = scan_offsets(off, n_reads, &max_len)) return rc;
+    if (!seqs && total_bases) {
+        set_error("colbwt_query: null sequence buffer");
+        return COLBWT_ERR_ARG;
+    }
+    // the compact form carries no lengths, so the narrowest PML type that holds the longest read serves on the device
+    const int pml_width = compact_api ? (max_len < 256 ? COLBWT_PML_U8 : max_len < 65536 ? COLBWT_PML_U16 : COLBWT_PML_U32) : cs.pml_width;
+    if (int rc = check_width(pml_width, max_len)) return rc;
+    // pageable result buffers are reached through one pinned staging area per slot
+    const bool pageable_out = !compact_api && !(is_pinned(cs.pml) && is_pinned(cs.cid));
+    const Geometry geo = chunk_geometry(total_bases, n_reads, max_len, pageable_out ? (uint64_t)(pml_width + 1) : 0);
+
+    std::lock_guard<std::mutex> guard(idx->query_mutex);
+    // ---- where to pack and how to cross the link: measured, not guessed -------------------------------------------
+    // Mode bit 0: reads packed on the device (raw bytes DMA-ed as they are; needs a pinned input and no read that will be
+    // split into chunk tasks).  Mode bit 1 (dense results only): compact transport.  One B200 fed by 16 cores: host packing
+    // 19.5-22.7 Gbases/s end to end, device packing 17.0 (the extra 1 B/base of H2D slows the D2H stream on the shared
+    // link); with few threads per process (one rank per GPU on a 32-core box) the host packer falls behind the link.  The
+    // first large call follows a rule, every other allowed mode is then tried once, later calls take the fastest (5 %
+    // hysteresis in favour of the rule).  COLBWT_DEVICE_PACK / COLBWT_COMPACT_D2H pin a bit.
+    const SplitParams sp_query = SplitParams::from_env();
+    const bool can_device_pack = is_pinned(seqs) && max_len < sp_query.min_len;
+    const bool large_call = total_bases >= (64ull << 20);
+    uint32_t allowed = 0;
+    for (int m = 0; m < 4; ++m) {
+        if ((m & 1) && !can_device_pack) continue;
+        if ((m & 2) && compact_api) continue;
+        allowed |= 1u << m;
+    }
+    auto pin_bit = [&](const char *name, int bit) {
+        const char *e = getenv(name);
+        if (!e) return;
+        uint32_t keep = 0;
+        for (int m = 0; m < 4; ++m)
+            if (((m >> bit) & 1) == (atoi(e) != 0 ? 1 : 0)) keep |= 1u << m;
+        if (allowed & keep) allowed &= keep;
+    };
+    pin_bit("COLBWT_DEVICE_PACK", 0);
+    pin_bit("COLBWT_COMPACT_D2H", 1);
+    double *rates = idx->mode_rate[compact_api ? 1 : 0];
+    int rule = (Pool::get().size() < 8) ? 1 : 0;
+    const int mode = choose_mode(rule, allowed, rates, 4, large_call);   // tasks.h
+    const bool device_pack = (mode & 1) != 0;
+    const OutKind kind = compact_api ? OUT_COMPACT : ((mode & 2) ? OUT_DENSE_VIA_COMPACT : OUT_DENSE);
+    idx->last_packing = device_pack ? 1 : 0;
+    idx->last_transport = kind == OUT_DENSE ? 0 : 1;
+
+    Pipeline *plp = nullptr;
+    const bool staged_out = pageable_out && kind == OUT_DENSE;
+    const Pipeline *before = idx->pipeline;
+    if (int rc = get_pipeline(idx, geo.chunk_reads, geo.chunk_bases, pml_width, staged_out, kind != OUT_DENSE, &plp)) return rc;
+    const bool fresh_pipeline = plp != before;   // this call pays for the staging allocations: not a timing sample
+
+    QueryJob J;
+    J.idx = idx;
+    J.pl = plp;
+    J.seqs = seqs;
+    J.off = off;
+    J.n_reads = n_reads;
+    J.pml_width = pml_width;
+    J.kind = kind;
+    J.device_pack = device_pack;
+    J.staged_out = staged_out;
+    J.pml = (uint8_t *)cs.pml;
+    J.cid = cs.cid;
+    J.trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
+    plan_chunks(off, n_reads, geo, J.chunks);
+    const int n_dev = (int)idx->dev.size();
+    J.times.resize((size_t)n_dev);
+    if (compact_api) {
+        // result buffer: header | directory | fixed parts | value regions (bump-allocated as the chunks complete)
+        J.cbuf = (uint8_t *)cs.cbuf;
+        J.ccap = cs.ccap;
+        J.cbuf_pinned = is_pinned(cs.cbuf);
+        uint64_t at = sizeof(colbwt_compact_header) + J.chunks.size() * sizeof(colbwt_compact_segment);
+        at = (at + 15) & ~15ull;
+        const uint64_t dir_end = at;
+        if (dir_end > J.ccap) {
+            set_error("colbwt_query_compact: result buffer of %zu bytes cannot hold the directory of %zu segments", J.ccap, J.chunks.size());
+            return COLBWT_ERR_NOMEM;
+        }
+        J.segments = reinterpret_cast<colbwt_compact_segment *>(J.cbuf + sizeof(colbwt_compact_header));
+        for (size_t i = 0; i < J.chunks.size(); ++i) {
+            const Chunk &c = J.chunks[i];
+            const CompactLayout lay(off[c.r1] - off[c.r0]);
+            colbwt_compact_segment sg{};
+            sg.first_read = c.r0;
+            sg.n_reads = c.r1 - c.r0;
+            sg.first_base = off[c.r0] - off[0];
+            sg.n_bases = off[c.r1] - off[c.r0];
+            sg.match_off = at + lay.match_off;
+            sg.cid_off = at + lay.cid_off;
+            sg.prefix_off = at + lay.prefix_off;
+            J.segments[i] = sg;
+            at += sg.n_bases ? lay.fixed_bytes : 0;
+        }
+        if (at > J.ccap) {
+            set_error("colbwt_query_compact: result buffer of %zu bytes is too small (%llu needed before any chain id)", J.ccap, (unsigned long long)at);
+            return COLBWT_ERR_NOMEM;
+        }
+        J.values_cursor.store(at);
+    }
+    struct OriginEvent {   // COLBWT_TRACE=2 (single device): timeline origin
+        cudaEvent_t e = nullptr;
+        ~OriginEvent() { if (e) cudaEventDestroy(e); }
+    } origin;
+    if (J.trace >= 2 && n_dev == 1) {
+        CB_CUDA(cudaSetDevice(idx->dev[0].device));
+        CB_CUDA(cudaEventCreate(&origin.e));
+        CB_CUDA(cudaEventRecord(origin.e, plp->slots[0].stream));
+        J.origin = origin.e;
+    } else if (J.trace >= 2) {
+        J.trace = 1;   // events of different devices cannot be compared: per-device summaries only
+    }
+
+    const double t_begin = now_s();
+    if (n_dev == 1) {
+        feed_device(J, 0);
+    } else {
+        std::vector<std::thread> feeders;
+        for (int d = 0; d < n_dev; ++d) feeders.emplace_back([&J, d] { feed_device(J, d); });
+        for (auto &t : feeders) t.join();
+    }
+    const double t_total = now_s() - t_begin;
+    if (J.rc.load() != COLBWT_OK) {
+        set_error("%s", J.err.c_str());
+        return J.rc.load();
+    }
+    if (compact_api) {
+        colbwt_compact_header h{};
+        h.magic = COLBWT_COMPACT_MAGIC;
+        h.n_segments = J.chunks.size();
+        h.n_reads = n_reads;
+        h.n_bases = total_bases;
+        h.bytes_used = J.values_cursor.load();
+        memcpy(J.cbuf, &h, sizeof(h));
+        if (cs.cused) *cs.cused = (size_t)h.bytes_used;
+    }
+    if (J.trace >= 2 && !J.timeline.empty()) {
+        float h2d = 0, ker = 0, d2h = 0;
+        for (auto &c : J.timeline) { h2d += c.k0 - c.h2d0; ker += c.d2h0 - c.k0; d2h += c.end - c.d2h0; }
+        fprintf(stderr, "[colbwt_query] stream time per stage, summed over chunks: H2D %.1f ms, kernel %.1f ms, D2H %.1f ms; last chunk ends at %.1f ms\n",
+                h2d, ker, d2h, J.timeline.back().end);
+        for (size_t i = 0; i < J.timeline.size(); i += std::max<size_t>(1, J.timeline.size() / 8))
+            fprintf(stderr, "    chunk %3zu: H2D %.2f..%.2f kernel ..%.2f D2H ..%.2f ms\n", i, J.timeline[i].h2d0, J.timeline[i].k0, J.timeline[i].d2h0, J.timeline[i].end);
+    }
+    if (J.trace) {
+        for (int d = 0; d < n_dev; ++d) {
+            const QueryJob::DevTimes &tm = J.times[(size_t)d];
+            fprintf(stderr, "[colbwt_query] device %d: %llu chunks: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, host post-processing %.1f ms, loop %.1f ms\n",
+                    idx->dev[(size_t)d].device, (unsigned long long)tm.chunks, tm.pack * 1e3, tm.wait * 1e3, tm.enqueue * 1e3, tm.post * 1e3, tm.loop * 1e3);
+        }
+        fprintf(stderr, "[colbwt_query] %zu chunks, %.1f Mbases, total %.1f ms = %.2f Gbases/s (%s, packing on the %s, %d host threads)\n", J.chunks.size(),
+                total_bases / 1e6, t_total * 1e3, total_bases / t_total / 1e9,
+                kind == OUT_DENSE ? (staged_out ? "dense via staging" : "dense into pinned buffers") : kind == OUT_COMPACT ? "compact result" : "dense, compact transport",
+                device_pack ? "device" : "host", Pool::get().size());
+    }
+    if (large_call && !fresh_pipeline) rates[mode] = (double)total_bases / std::max(1e-9, t_total);
+    return COLBWT_OK;
+}
+
+static int run_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, const CallSpec &cs)
+{
+    const int rc = query_impl(idx, seqs, off, n_reads, cs);
+    if (rc != COLBWT_OK && rc != COLBWT_ERR_ARG && idx->pipeline) {
         // a failed copy or launch may leave chunks in flight: wait, then drop the staging pipeline so that the next
         // call starts from a clean one
+        std::string msg = colbwt_last_error();
         std::lock_guard<std::mutex> guard(idx->query_mutex);
         for (auto &d : idx->dev) {
             cudaSetDevice(d.device);
@@ -608,225 +1138,117 @@ extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64
         cudaGetLastError();
         destroy_pipeline(idx->pipeline);
         idx->pipeline = nullptr;
+        set_error("%s", msg.c_str());
     }
     return rc;
 }
 
-static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid)
+} // namespace colbwt
+
+extern "C" int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
+                            void *pml, int pml_width, uint8_t *cid)
 {
     if (!idx || !off || !pml || !cid || idx->dev.empty()) {
         set_error("colbwt_query: bad argument");
         return COLBWT_ERR_ARG;
     }
     if (n_reads == 0) return COLBWT_OK;
-    const uint64_t total_bases = off[n_reads] - off[0];
-    // chunk geometry
-    uint64_t chunk_bases = 96ull << 20;   // measured on C2 (profiles/r1/e2e_chunk_sweep.log): 16/24/32/48/96/128/192 M -> 83.6/85.0/81.1/76.3/71.8-73.2/72.0/73.1 ms
-    if (const char *e = getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    // one pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB
+    CallSpec cs;
+    cs.kind = OUT_DENSE;
+    cs.pml = pml;
+    cs.pml_width = pml_width;
+    cs.cid = cid;
+    return run_query(idx, seqs, off, n_reads, cs);
+}
+
+extern "C" int colbwt_query_compact(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
+                                    void *result, size_t capacity, size_t *bytes_used)
+{
+    if (!idx || !off || !result || capacity < sizeof(colbwt_compact_header) || idx->dev.empty()) {
+        set_error("colbwt_query_compact: bad argument");
+        return COLBWT_ERR_ARG;
+    }
+    if (n_reads == 0) {
+        colbwt_compact_header h{};
+        h.magic = COLBWT_COMPACT_MAGIC;
+        h.bytes_used = sizeof(h);
+        memcpy(result, &h, sizeof(h));
+        if (bytes_used) *bytes_used = sizeof(h);
+        return COLBWT_OK;
+    }
+    CallSpec cs;
+    cs.kind = OUT_COMPACT;
+    cs.cbuf = result;
+    cs.ccap = capacity;
+    cs.cused = bytes_used;
+    return run_query(idx, seqs, off, n_reads, cs);
+}
+
+extern "C" size_t colbwt_compact_bound(const uint64_t *off, uint64_t n_reads)
+{
+    if (!off || n_reads == 0) return sizeof(colbwt_compact_header);
     uint32_t max_len = 0;
-    {
-        const int T = n_reads >= (1u << 16) ? Pool::get().size() : 1;
-        std::vector<uint64_t> part_max((size_t)T, 0), part_bad((size_t)T, UINT64_MAX);
-        Pool::get().parallel_for(T, [&](int t) {
-            const uint64_t a = n_reads * (uint64_t)t / (uint64_t)T, b = n_reads * (uint64_t)(t + 1) / (uint64_t)T;
-            uint64_t mx = 0, bad = UINT64_MAX;
-            for (uint64_t i = a; i < b; ++i) {
-                if (off[i + 1] < off[i]) bad = std::min(bad, i);
-                else mx = std::max(mx, off[i + 1] - off[i]);
-            }
-            part_max[(size_t)t] = mx;
-            part_bad[(size_t)t] = bad;
-        });
-        const uint64_t bad = *std::min_element(part_bad.begin(), part_bad.end());
-        if (bad != UINT64_MAX) {
-            set_error("colbwt_query: offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
+    if (scan_offsets(off, n_reads, &max_len) != COLBWT_OK) return 0;
+    const uint64_t total = off[n_reads] - off[0];
+    const Geometry geo = chunk_geometry(total, n_reads, max_len, 0);
+    std::vector<Chunk> chunks;
+    plan_chunks(off, n_reads, geo, chunks);
+    uint64_t at = (sizeof(colbwt_compact_header) + chunks.size() * sizeof(colbwt_compact_segment) + 15) & ~15ull;
+    for (const Chunk &c : chunks) {
+        const uint64_t nb = off[c.r1] - off[c.r0];
+        at += (nb ? CompactLayout(nb).fixed_bytes : 0) + ((nb + 15) & ~15ull);   // every chain id non-zero
+    }
+    return (size_t)at;
+}
+
+extern "C" int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid)
+{
+    if (!result || !off || !pml || !cid) {
+        set_error("colbwt_compact_expand: null argument");
+        return COLBWT_ERR_ARG;
+    }
+    colbwt_compact_header h;
+    memcpy(&h, result, sizeof(h));
+    if (h.magic != COLBWT_COMPACT_MAGIC || h.n_reads != n_reads || (n_reads && h.n_bases != off[n_reads] - off[0])) {
+        set_error("colbwt_compact_expand: not a compact result of these %llu reads", (unsigned long long)n_reads);
+        return COLBWT_ERR_ARG;
+    }
+    if (pml_width != COLBWT_PML_U8 && pml_width != COLBWT_PML_U16 && pml_width != COLBWT_PML_U32) {
+        set_error("pml_width must be 1, 2 or 4");
+        return COLBWT_ERR_ARG;
+    }
+    const uint8_t *buf = (const uint8_t *)result;
+    const colbwt_compact_segment *segs = reinterpret_cast<const colbwt_compact_segment *>(buf + sizeof(colbwt_compact_header));
+    Pool &pool = Pool::get();
+    for (uint64_t s = 0; s < h.n_segments; ++s) {
+        const colbwt_compact_segment &sg = segs[s];
+        if (sg.first_read + sg.n_reads > n_reads || off[sg.first_read] - off[0] != sg.first_base || off[sg.first_read + sg.n_reads] - off[sg.first_read] != sg.n_bases) {
+            set_error("colbwt_compact_expand: segment %llu does not match the offsets", (unsigned long long)s);
             return COLBWT_ERR_ARG;
         }
-        max_len = (uint32_t)std::min<uint64_t>(*std::max_element(part_max.begin(), part_max.end()), 0xFFFFFFFFull);
-    }
-    if (!seqs && total_bases) {
-        set_error("colbwt_query: null sequence buffer");
-        return COLBWT_ERR_ARG;
-    }
-    if (max_len == 0xFFFFFFFFu) {
-        set_error("a read of 2^32-1 or more bases is not supported");
-        return COLBWT_ERR_ARG;
-    }
-    if (int rc = check_width(pml_width, max_len)) return rc;
-    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read at a time and
-    // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
-    if (!getenv("COLBWT_CHUNK_BASES"))
-        chunk_bases = std::max<uint64_t>(chunk_bases, std::min<uint64_t>(512ull << 20, (total_bases / n_reads) * 32768));
-    // pageable result buffers are reached through one pinned staging area per slot: keep each under 256 MB
-    const bool pageable_out = !(is_pinned(pml) && is_pinned(cid));
-    if (pageable_out && !getenv("COLBWT_CHUNK_BASES")) chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / (uint64_t)(pml_width + 1));
-    chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
-    chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
-    // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
-    const uint64_t chunk_reads = std::min<uint64_t>(std::max<uint64_t>(chunk_bases / 32, 1024), n_reads);
-
-    const int n_dev = (int)idx->dev.size();
-    std::lock_guard<std::mutex> guard(idx->query_mutex);
-    Pipeline *plp = nullptr;
-    const bool staged_out = pageable_out;
-    const Pipeline *before = idx->pipeline;
-    if (int rc = get_pipeline(idx, chunk_reads, chunk_bases, pml_width, staged_out, &plp)) return rc;
-    const bool fresh_pipeline = plp != before;   // this call pays for the staging allocations: not a timing sample
-    Pipeline &pl = *plp;
-    // Pack on the device when the input can be DMA-ed as it is (pinned) and no read will be split into chunk tasks:
-    // H2D has headroom (the link is busy in the other direction), host cores often do not (one process per GPU).
-    const SplitParams sp_query = SplitParams::from_env();
-    const char *dp_env = getenv("COLBWT_DEVICE_PACK");
-    // Where to pack is measured, not guessed.  One B200 fed by 16 cores: host 19.5-22.7 Gbases/s end to end, device 17.0 (the
-    // extra 1 B/base of H2D slows the D2H stream on the shared link); two ranks with 8 threads each: 37.7 against 34.8;
-    // with fewer threads per process the host packer (2.6 Gbases/s per thread) falls behind the link.  So: the first large
-    // timed call follows a rule (device iff fewer than 4 packing threads), the next tries the other way once, later calls
-    // take the faster of the two (5 % hysteresis) and re-try the other one every 64th large call.  COLBWT_DEVICE_PACK
-    // pins the choice.
-    const bool can_device_pack = is_pinned(seqs) && max_len < sp_query.min_len;
-    const bool large_call = total_bases >= (64ull << 20);
-    bool device_pack = false;
-    if (dp_env) {
-        device_pack = atoi(dp_env) != 0 && can_device_pack;
-    } else if (can_device_pack) {
-        device_pack = choose_device_pack(Pool::get().size() < 4 ? 1 : 0, idx->pack_rate, large_call, idx->large_calls);   // tasks.h
-    }
-    idx->last_packing = device_pack ? 1 : 0;
-
-    static const int trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
-    struct ChunkTimes { float h2d0, k0, d2h0, end; };
-    std::vector<ChunkTimes> timeline;
-    cudaEvent_t ev_origin = nullptr;
-    if (trace >= 2) {
-        CB_CUDA(cudaSetDevice(idx->dev[0].device));
-        CB_CUDA(cudaEventCreate(&ev_origin));
-        CB_CUDA(cudaEventRecord(ev_origin, pl.slots[0].stream));
-    }
-    uint8_t *pml_out = (uint8_t *)pml;
-    auto drain = [&](Slot &k) -> int {   // wait for the slot's previous chunk; copy out if staged
-        if (!k.pending) return COLBWT_OK;
-        CB_CUDA(cudaEventSynchronize(k.done));
-        if (trace >= 2) {
-            ChunkTimes ct{};
-            cudaEventElapsedTime(&ct.h2d0, ev_origin, k.tev[0]);
-            cudaEventElapsedTime(&ct.k0, ev_origin, k.tev[1]);
-            cudaEventElapsedTime(&ct.d2h0, ev_origin, k.tev[2]);
-            cudaEventElapsedTime(&ct.end, ev_origin, k.tev[3]);
-            timeline.push_back(ct);
+        if (!sg.n_bases) continue;
+        const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, sg.n_bases >> 16));
+        const std::vector<uint64_t> cut = slice_reads(off, sg.first_read, sg.first_read + sg.n_reads, T);
+        std::atomic<bool> too_long{false};
+        pool.parallel_for(T, [&](int t) {
+            if (pml_width < 4)
+                for (uint64_t i = cut[(size_t)t]; i < cut[(size_t)t + 1]; ++i)
+                    if (off[i + 1] - off[i] > (pml_width == 1 ? 255u : 65535u)) too_long = true;
+            if (too_long) return;
+            expand_reads(reinterpret_cast<const uint32_t *>(buf + sg.match_off), reinterpret_cast<const uint32_t *>(buf + sg.cid_off),
+                         reinterpret_cast<const uint32_t *>(buf + sg.prefix_off), buf + sg.values_off, off, sg.first_read, cut[(size_t)t], cut[(size_t)t + 1],
+                         (uint8_t *)pml + sg.first_base * (uint64_t)pml_width, pml_width, cid + sg.first_base);
+        });
+        if (too_long) {
+            set_error("colbwt_compact_expand: a read does not fit %d-byte PML values", pml_width);
+            return COLBWT_ERR_ARG;
         }
-        if (staged_out) {   // pageable destination: copy out with all packing threads (first-touch page faults included)
-            uint8_t *dst[2] = {pml_out + k.out_base * (uint64_t)pml_width, cid + k.out_base};
-            const uint8_t *src[2] = {k.h_out, k.h_out + pl.cap_bases * (uint64_t)pml_width + 32};
-            const uint64_t bytes[2] = {k.out_bases * (uint64_t)pml_width, k.out_bases};
-            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)Pool::get().size(), (bytes[0] + bytes[1]) >> 20));
-            Pool::get().parallel_for(2 * T, [&](int i) {
-                const int a = i / T, t = i % T;
-                const uint64_t lo = bytes[a] * (uint64_t)t / (uint64_t)T, hi = bytes[a] * (uint64_t)(t + 1) / (uint64_t)T;
-                memcpy(dst[a] + lo, src[a] + lo, hi - lo);
-            });
-        }
-        k.pending = false;
-        return COLBWT_OK;
-    };
-
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_pack = 0, t_drain = 0, t_enqueue = 0;
-    const double t_begin = now();
-    uint64_t r0 = 0, chunk_no = 0;
-    while (r0 < n_reads) {
-        // next chunk [r0, r1): at most chunk_bases bases and chunk_reads reads, at least one read
-        uint64_t r1 = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + chunk_bases) - off) - 1;
-        r1 = std::min(r1, r0 + chunk_reads);
-        if (r1 <= r0) r1 = r0 + 1;
-        const int d = (int)(chunk_no % (uint64_t)n_dev);
-        Slot &k = pl.slots[(size_t)d * SLOTS_PER_DEVICE + (size_t)((chunk_no / (uint64_t)n_dev) % SLOTS_PER_DEVICE)];
-        const DeviceTable &dt = idx->dev[d];
-        CB_CUDA(cudaSetDevice(dt.device));
-        double t0 = now();
-        if (int rc = drain(k)) return rc;
-        t_drain += now() - t0;
-        t0 = now();
-
-        Staging st;
-        st.meta = k.h_meta;
-        st.meta_b = k.h_meta_b;
-        st.words = k.h_words;
-        st.bytes = k.h_bytes;
-        if (device_pack) prepare_offsets_only(off, r0, r1, st);
-        else prepare_reads(seqs, off, r0, r1, off[n_reads], (uint64_t)dt.sm_count * 1024 / (uint64_t)std::min<int>(SLOTS_PER_DEVICE, 4), st);
-        t_pack += now() - t0;
-        t0 = now();
-
-        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[0], k.stream));
-        CB_CUDA(cudaMemcpyAsync(k.d_meta, k.h_meta, st.n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
-        if (device_pack) {
-            CB_CUDA(cudaMemcpyAsync(k.d_bytes, seqs + off[r0], st.n_bases, cudaMemcpyHostToDevice, k.stream));
-            if (int rc = launch_pack(dt, k.d_bytes, k.d_meta, (uint32_t)st.n_reads, k.d_words, k.d_meta_b, (uint32_t *)(k.d_cursors + 3), k.stream)) return rc;
-        } else {
-            CB_CUDA(cudaMemcpyAsync(k.d_words, k.h_words, st.n_words * 4, cudaMemcpyHostToDevice, k.stream));
-            if (st.n_irregular) {
-                CB_CUDA(cudaMemcpyAsync(k.d_meta_b, k.h_meta_b, st.n_irregular * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
-                CB_CUDA(cudaMemcpyAsync(k.d_bytes, k.h_bytes, st.n_byte_bases, cudaMemcpyHostToDevice, k.stream));
-            }
-        }
-        BatchView bv{};
-        bv.meta = k.d_meta;
-        bv.meta_b = k.d_meta_b;
-        bv.words = k.d_words;
-        bv.bytes = k.d_bytes;
-        bv.pml = k.d_pml;
-        bv.cid = k.d_cid;
-        bv.n_packed = (uint32_t)st.n_reads;
-        bv.n_bytes = (uint32_t)st.n_irregular;
-        bv.n_bytes_dev = device_pack ? (const uint32_t *)(k.d_cursors + 3) : nullptr;
-        if (int rc = upload_plan(st.plan, k.plan, bv, k.stream)) return rc;
-        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[1], k.stream));
-        if (int rc = launch_traverse(dt, bv, pml_width, k.d_cursors, k.stream)) return rc;
-        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
-        const uint64_t ob = off[r0] - off[0];
-        if (staged_out) {
-            CB_CUDA(cudaMemcpyAsync(k.h_out, k.d_pml, st.n_bases * (uint64_t)pml_width, cudaMemcpyDeviceToHost, k.stream));
-            CB_CUDA(cudaMemcpyAsync(k.h_out + pl.cap_bases * (uint64_t)pml_width + 32, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
-        } else {
-            CB_CUDA(cudaMemcpyAsync(pml_out + ob * (uint64_t)pml_width, k.d_pml, st.n_bases * (uint64_t)pml_width, cudaMemcpyDeviceToHost, k.stream));
-            CB_CUDA(cudaMemcpyAsync(cid + ob, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
-        }
-        if (trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
-        CB_CUDA(cudaEventRecord(k.done, k.stream));
-        k.pending = true;
-        k.out_base = ob;
-        k.out_bases = st.n_bases;
-        r0 = r1;
-        ++chunk_no;
-        t_enqueue += now() - t0;
-    }
-    const double t_loop = now() - t_begin;
-    for (size_t s = 0; s < pl.slots.size(); ++s) {
-        CB_CUDA(cudaSetDevice(idx->dev[s / SLOTS_PER_DEVICE].device));
-        if (int rc = drain(pl.slots[s])) return rc;
-    }
-    if (trace >= 2 && n_dev == 1) {
-        float h2d = 0, ker = 0, d2h = 0;
-        for (auto &c : timeline) { h2d += c.k0 - c.h2d0; ker += c.d2h0 - c.k0; d2h += c.end - c.d2h0; }
-        fprintf(stderr, "[colbwt_query] stream time per stage, summed over chunks: H2D %.1f ms, kernel %.1f ms, D2H %.1f ms; last chunk ends at %.1f ms\n",
-                h2d, ker, d2h, timeline.empty() ? 0.f : timeline.back().end);
-        for (size_t i = 0; i < timeline.size(); i += std::max<size_t>(1, timeline.size() / 8))
-            fprintf(stderr, "    chunk %3zu: H2D %.2f..%.2f kernel ..%.2f D2H ..%.2f ms\n", i, timeline[i].h2d0, timeline[i].k0, timeline[i].d2h0, timeline[i].end);
-    }
-    if (ev_origin) cudaEventDestroy(ev_origin);
-    if (trace)
-        fprintf(stderr, "[colbwt_query] %llu chunks, %.1f Mbases: pack %.1f ms, wait-for-slot %.1f ms, enqueue %.1f ms, loop %.1f ms, total %.1f ms (%s outputs, packing on the %s)\n",
-                (unsigned long long)chunk_no, total_bases / 1e6, t_pack * 1e3, t_drain * 1e3, t_enqueue * 1e3, t_loop * 1e3,
-                (now() - t_begin) * 1e3, staged_out ? "staged" : "pinned", device_pack ? "device" : "host");
-    if (large_call && !dp_env && can_device_pack && !fresh_pipeline) {
-        idx->pack_rate[device_pack ? 1 : 0] = (double)total_bases / std::max(1e-9, now() - t_begin);
-        ++idx->large_calls;
     }
     return COLBWT_OK;
 }
 
 extern "C" int colbwt_index_last_packing(const colbwt_index *idx) { return idx ? idx->last_packing : -1; }
+extern "C" int colbwt_index_last_transport(const colbwt_index *idx) { return idx ? idx->last_transport : -1; }
 
 extern "C" void *colbwt_host_alloc(size_t bytes)
 {

@@ -34,18 +34,33 @@ struct SplitParams {
     }
 };
 
-// Where colbwt_query packs the reads of a call that could go either way (pinned input, short reads).  rate[0] / rate[1] =
-// bases/s of the last large call packed on the host / on the device (0 = not measured yet); `rule` = the starting guess.
-// Large calls: measure the rule first, then the other way once, then keep the faster (5 % hysteresis, ties -> rule) and
-// try the other one again on every 64th large call.  Small calls follow what the large ones found.
-inline bool choose_device_pack(int rule, const double rate[2], bool large_call, uint32_t large_calls)
+// How colbwt_query runs a call that could go several ways (query.cu: where the reads are packed, how the results cross
+// the link).  rate[m] = bases/s of the last large call run in mode m (0 = not measured yet); `allowed` = bit mask of the
+// modes this call can use; `rule` = the starting guess.  Large calls: the rule first, then every other allowed mode once,
+// then the fastest -- the rule keeps its place unless another mode is more than 5 % faster.  Small calls follow what
+// the large ones found.  No periodic re-trial: a process that shares the host with seven others (one rank per GPU) would
+// only sample noise.
+inline int choose_mode(int rule, uint32_t allowed, const double *rate, int n_modes, bool large_call)
 {
+    if (!(allowed & (1u << rule))) {
+        // the rule is not available to this call: keep what it can of the rule (its low bits), else the lowest allowed mode
+        int pick = -1;
+        for (int m = 0; m < n_modes && pick < 0; ++m)
+            if ((allowed & (1u << m)) && (m & 1) == (rule & 1)) pick = m;
+        for (int m = 0; m < n_modes && pick < 0; ++m)
+            if (allowed & (1u << m)) pick = m;
+        rule = pick < 0 ? 0 : pick;
+    }
+    if (large_call) {
+        if (rate[rule] == 0) return rule;
+        for (int m = 0; m < n_modes; ++m)
+            if ((allowed & (1u << m)) && rate[m] == 0) return m;
+    }
     int best = rule;
-    if (rate[0] > 0 && rate[1] > 0) best = rate[1] > 1.05 * rate[0] ? 1 : (rate[0] > 1.05 * rate[1] ? 0 : rule);
-    if (!large_call) return best != 0;
-    if (rate[rule] == 0) return rule != 0;
-    if (rate[1 - rule] == 0) return rule == 0;
-    return (large_calls % 64 == 63) ? best == 0 : best != 0;
+    if (rate[rule] > 0)
+        for (int m = 0; m < n_modes; ++m)
+            if ((allowed & (1u << m)) && rate[m] > 1.05 * rate[rule] && rate[m] > rate[best]) best = m;
+    return best;
 }
 
 struct TaskPlan {

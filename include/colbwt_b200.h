@@ -16,6 +16,9 @@
  *   colbwt_index_stats       col_bwt::bwt_stats / runs / size        include/col_bwt.hpp:331-344
  *   colbwt_query             col_pml::query_pml(const char*, size_t) include/col_bwt.hpp:409-412, for a whole
  *                            batch of reads (the per-read loop of src/pml_query.cpp:74-86)
+ *   colbwt_query_compact     the same result in compact form (one match bit per base + the non-zero chain ids) for
+ *                            consumers that do not need dense arrays; colbwt_compact_expand rebuilds the dense
+ *                            arrays of col_pml::query_pml from it bit-exactly
  *   colbwt_batch_*           the same split into upload / traverse / download so the traversal can be
  *                            timed with its inputs resident in HBM
  *   colbwt_format_stats      the text writer of pml_to_vec           src/pml_query.cpp:79-85
@@ -45,7 +48,7 @@ typedef enum colbwt_status {
     COLBWT_ERR_ROW_TOO_LONG = -3,/* a row of >= 65536 symbols (16-bit offset field wraps in the reference, LF_table.hpp:39) */
     COLBWT_ERR_CUDA = -4,        /* no device / CUDA runtime failure                        */
     COLBWT_ERR_ARG = -5,         /* bad argument (null pointer, PML width too small, ...)   */
-    COLBWT_ERR_NOMEM = -6
+    COLBWT_ERR_NOMEM = -6        /* allocation failed, or a caller buffer is too small      */
 } colbwt_status;
 
 typedef struct colbwt_index colbwt_index;   /* move table replicated in the HBM of one or more GPUs */
@@ -114,10 +117,45 @@ void colbwt_index_free(colbwt_index *idx);
 int colbwt_query(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                  void *pml, int pml_width, uint8_t *cid);
 
+/* ---- query, compact result ------------------------------------------------------------------------------
+ * The dense result of col_pml::query_pml (include/col_bwt.hpp:409-412) is highly redundant: the length is reset to 0 on a
+ * mismatch and incremented on a match (col_bwt.hpp:516-523), so a read's PML array is a function of one match bit per
+ * base (PML[j] = distance from j to the first mismatch at or right of j, or to the end of the read), and chain ids are 0
+ * off the marked sub-runs.  The compact result holds exactly that -- about 0.3 bytes per base on BASELINE configs[1]
+ * instead of 2-5 -- so PCIe stops bounding the call.  Layout of the caller's buffer (all offsets in bytes from its start):
+ *   colbwt_compact_header | colbwt_compact_segment[n_segments] | per segment: match words, chain-id words, prefix | values
+ * A segment covers consecutive reads; bit b of word w (u32, little endian) of its match / chain-id words refers to base
+ * 32w+b counted from the segment's first base; prefix[g] (u32) = number of non-zero chain ids before base 2048g of the
+ * segment, prefix[ceil(n_bases/2048)] = n_values; values = the non-zero chain ids (u8) in base order. */
+#define COLBWT_COMPACT_MAGIC 0x31504d4354574243ull   /* "CBWTCMP1" */
+typedef struct colbwt_compact_header {
+    uint64_t magic, n_segments, n_reads, n_bases, bytes_used, reserved[3];
+} colbwt_compact_header;
+typedef struct colbwt_compact_segment {
+    uint64_t first_read, n_reads;     /* reads [first_read, first_read + n_reads) of the call                    */
+    uint64_t first_base, n_bases;     /* first_base = off[first_read] - off[0]                                   */
+    uint64_t match_off, cid_off;      /* ceil(n_bases/32) u32 words each                                         */
+    uint64_t prefix_off;              /* ceil(n_bases/2048) + 1 u32 entries                                      */
+    uint64_t values_off, n_values;
+} colbwt_compact_segment;
+
+/* Bytes that always suffice for colbwt_query_compact on these reads (every chain id non-zero); 0 on bad offsets. */
+size_t colbwt_compact_bound(const uint64_t *off, uint64_t n_reads);
+/* Same reads, same traversal as colbwt_query; `result` (capacity bytes, ideally pinned: then the GPU writes into it
+ * directly) receives the compact form.  COLBWT_ERR_NOMEM if it does not fit.  *bytes_used (may be NULL) = bytes written. */
+int colbwt_query_compact(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
+                         void *result, size_t capacity, size_t *bytes_used);
+/* Host-side: rebuild the dense arrays colbwt_query would have returned (pml_width-byte PML, u8 chain ids) for the
+ * same reads.  Runs on the library's host threads; needs no GPU. */
+int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid);
+
 /* Where the last colbwt_query on this index packed the reads into 2 bits per base: 0 on the host, 1 on the device (raw
  * bytes copied as they are; only when `seqs` is pinned and the reads are short).  The library measures both ways on large
  * calls and keeps the faster one; COLBWT_DEVICE_PACK=0|1 pins the choice.  No reference counterpart (diagnostic). */
 int colbwt_index_last_packing(const colbwt_index *idx);
+/* How the dense results of the last colbwt_query crossed the link: 0 as they are, 1 in the compact form above, expanded
+ * into the caller's arrays by the library's host threads (measured the same way; COLBWT_COMPACT_D2H=0|1 pins it). */
+int colbwt_index_last_transport(const colbwt_index *idx);
 
 /* Pinned host memory for seqs / pml / cid buffers (lets colbwt_query copy without a staging hop). */
 void *colbwt_host_alloc(size_t bytes);

@@ -214,10 +214,9 @@ uint32_t emu_plan(uint32_t len, uint32_t chunk, uint32_t warm, uint32_t *out, ui
     return (uint32_t)plan.by_slot.size();
 }
 
-int emu_choose_device_pack(int rule, double rate_host, double rate_device, int large_call, uint32_t large_calls)
+int emu_choose_mode(int rule, uint32_t allowed, const double *rate, int n_modes, int large_call)
 {
-    const double rate[2] = {rate_host, rate_device};
-    return choose_device_pack(rule, rate, large_call != 0, large_calls) ? 1 : 0;
+    return choose_mode(rule, allowed, rate, n_modes, large_call != 0);
 }
 int emu_pack(const uint8_t *seq, uint64_t len, uint32_t *words) { return pack_read_2bit(seq, len, words) ? 1 : 0; }
 uint64_t emu_slow_rows(EmuTable *t) { return t->slow_rows; }

@@ -247,21 +247,35 @@ def test_chunk_planner_tiles_the_read(length, chunk, warm):
     assert (t[:, 3] == np.arange(n)).all()
 
 
-def test_packing_choice_is_measured_then_kept():
-    """tasks.h: choose_device_pack -- the rule first, the other way once, then the faster one with hysteresis."""
+def test_mode_choice_is_measured_then_kept():
+    """tasks.h: choose_mode -- the rule first, every other allowed mode once, then the fastest (the rule keeps its place
+    within 5 %).  Modes of colbwt_query: bit 0 = reads packed on the device, bit 1 = compact transport."""
     import ctypes as C
     from emu import build, SO
     build()
     L = C.CDLL(SO)
-    L.emu_choose_device_pack.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint32]
-    f = lambda rule, h, d, large=1, calls=0: bool(L.emu_choose_device_pack(rule, h, d, large, calls))
+    L.emu_choose_mode.argtypes = [C.c_int, C.c_uint32, C.POINTER(C.c_double), C.c_int, C.c_int]
+
+    def f(rule, rates, allowed=0b1111, large=1):
+        arr = (C.c_double * 4)(*rates)
+        return L.emu_choose_mode(rule, allowed, arr, 4, large)
     for rule in (0, 1):
-        assert f(rule, 0, 0) == bool(rule)                   # nothing measured: the rule
-        assert f(rule, 0, 0, large=0) == bool(rule)
-        host_known, dev_known = (20e9, 0) if rule == 0 else (0, 17e9)
-        assert f(rule, host_known, dev_known) == (not rule)  # the rule was measured: try the other way once
-        assert f(rule, host_known, dev_known, large=0) == bool(rule)   # small calls never probe
-        assert f(rule, 20e9, 17e9) is False and f(rule, 6e9, 12e9) is True
-        assert f(rule, 20e9, 20.5e9) == bool(rule)           # within 5 %: stay with the rule
-        assert f(rule, 20e9, 17e9, calls=63) is True and f(rule, 6e9, 12e9, calls=127) is False   # periodic re-try
-        assert f(rule, 20e9, 17e9, large=0, calls=63) is False
+        assert f(rule, [0, 0, 0, 0]) == rule                      # nothing measured: the rule
+        assert f(rule, [0, 0, 0, 0], large=0) == rule
+        known = [0, 0, 0, 0]
+        known[rule] = 20e9
+        first_other = 1 - rule
+        assert f(rule, known) == first_other                      # the rule was measured: probe the next unmeasured mode
+        assert f(rule, known, large=0) == rule                    # small calls never probe
+        known[first_other] = 5e9
+        assert f(rule, known) == 2 and f(rule, known, allowed=0b0011) == rule   # only allowed modes are probed
+        assert f(rule, [20e9, 17e9, 30e9, 12e9]) == 2             # all measured: the fastest
+        r = [20e9] * 4
+        r[3] = 20.9e9
+        assert f(rule, r) == rule                                 # within 5 %: stay with the rule
+        r[3] = 22e9
+        assert f(rule, r) == 3 and f(rule, r, large=0) == 3       # small calls follow what the large ones found
+    # a rule this call cannot use (no pinned input -> no device packing): the host-packing modes are what is left
+    assert f(1, [0, 0, 0, 0], allowed=0b0101) == 0
+    assert f(1, [9e9, 0, 0, 0], allowed=0b0101) == 2
+    assert f(1, [9e9, 0, 12e9, 0], allowed=0b0101) == 2 and f(1, [9e9, 0, 9.2e9, 0], allowed=0b0101) == 0

@@ -522,3 +522,97 @@ def test_randomised_batches(cb, small_index, monkeypatch):
     for _ in range(30):
         ok, info = fz.one_round(cb, tbl, orc, rng, idx["text"], idx["seq_starts"], small_index["haps"])
         assert ok, info
+
+
+# ---- compact result form (compact.cu + expand.cpp) -------------------------------------------------------------------
+def _compact_cases(small_index):
+    idx = small_index["idx"]
+    extra, eoff = concat_reads(adversarial_reads(small_index["haps"]))
+    s, o = P.sample_reads(idx["text"], idx["seq_starts"], 120, 3000, sub=0.02, ins=0.015, dele=0.015, seed=16, len_jitter=0.5)
+    return [(small_index["seqs"], small_index["off"]), (extra, eoff), (s, o)]
+
+
+@pytest.mark.parametrize("chunk", [None, "20000"])
+def test_compact_result_expands_to_the_dense_arrays(cb, small_index, monkeypatch, chunk):
+    """colbwt_query_compact + colbwt_compact_expand == the oracle's dense arrays: one segment and many, pageable and pinned
+    result buffers, irregular and long reads."""
+    if chunk:
+        monkeypatch.setenv("COLBWT_CHUNK_BASES", chunk)
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    for seqs, off in _compact_cases(small_index):
+        want_p, want_c = orc.query_batch(seqs, off)
+        width = cb.PML_U16 if int(np.diff(off).max()) < 65536 else cb.PML_U32
+        res = tbl.query_compact(seqs, off)
+        segs = cb.compact_segments(res)
+        assert sum(s["n_reads"] for s in segs) == off.size - 1 and sum(s["n_bases"] for s in segs) == seqs.size
+        if chunk:
+            assert len(segs) > 1 or seqs.size <= 20000
+        assert sum(s["n_values"] for s in segs) == int((want_c != 0).sum())
+        pml, cid = cb.compact_expand(res, off, width)
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+        # pinned result buffer: the GPU writes into it directly
+        bound = cb._L.colbwt_compact_bound(off.ctypes.data, off.size - 1)
+        pin = cb.PinnedArray(bound, np.uint8)
+        res2 = tbl.query_compact(seqs, off, out=pin.array)
+        pml, cid = cb.compact_expand(res2, off, width)
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+        assert res2.size <= bound and res2.size < seqs.size + 4096      # far below the dense 3 bytes per base
+
+
+def test_compact_result_buffer_too_small_is_an_error(cb, small_index):
+    tbl = cb.ColPml.load(small_index["path"])
+    seqs, off = small_index["seqs"], small_index["off"]
+    with pytest.raises(cb.ColBwtError) as e:
+        tbl.query_compact(seqs, off, out=np.empty(seqs.size // 64, np.uint8))
+    assert e.value.code == -6
+    # the index is usable afterwards
+    res = tbl.query_compact(seqs, off)
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    pml, cid = cb.compact_expand(res, off, cb.PML_U16)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("device_pack", ["0", "1"])
+def test_dense_query_over_compact_transport(cb, small_index, monkeypatch, device_pack):
+    """COLBWT_COMPACT_D2H=1: dense results for the caller, compact form over the link, expanded by the host threads."""
+    monkeypatch.setenv("COLBWT_COMPACT_D2H", "1")
+    monkeypatch.setenv("COLBWT_DEVICE_PACK", device_pack)
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "50000")
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    for seqs, off in _compact_cases(small_index):
+        want_p, want_c = orc.query_batch(seqs, off)
+        widths = (cb.PML_U8, cb.PML_U16, cb.PML_U32) if int(np.diff(off).max()) < 256 else (cb.PML_U16, cb.PML_U32)
+        for width in widths:
+            pml, cid = tbl.query(seqs, off, width)                       # pageable buffers
+            assert tbl.last_transport == "compact"
+            assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+        h_seqs = cb.PinnedArray(seqs.size, np.uint8)                     # pinned input: device packing possible
+        h_seqs.array[:] = seqs
+        pp, pc = cb.PinnedArray(seqs.size, np.uint16), cb.PinnedArray(seqs.size, np.uint8)
+        tbl.query(h_seqs.array, off, cb.PML_U16, out=(pp.array, pc.array))
+        assert tbl.last_packing == ("device" if device_pack == "1" and int(np.diff(off).max()) < 8192 else "host")
+        assert np.array_equal(pp.array.astype(np.uint32), want_p) and np.array_equal(pc.array, want_c)
+    monkeypatch.setenv("COLBWT_COMPACT_D2H", "0")
+    pml, cid = tbl.query(seqs, off, cb.PML_U16)
+    assert tbl.last_transport == "dense"
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("compact", ["0", "1"])
+def test_two_replicas_on_one_gpu_feeder_threads(cb, small_index, monkeypatch, compact):
+    """Two replicas of the table on the SAME device: exercises the per-device feeder threads of colbwt_query (one per
+    replica, chunks taken from a shared counter) on a single-GPU box; results must land in input order."""
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "15000")
+    monkeypatch.setenv("COLBWT_COMPACT_D2H", compact)
+    seqs, off = small_index["seqs"], small_index["off"]
+    want_p, want_c = oracle.Oracle(small_index["path"]).query_batch(seqs, off)
+    tbl = cb.ColPml.load(small_index["path"], devices=[0, 0, 0])
+    assert tbl.stats.n_devices == 3
+    for _ in range(3):
+        pml, cid = tbl.query(seqs, off)
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    res = tbl.query_compact(seqs, off)
+    pml, cid = cb.compact_expand(res, off, cb.PML_U16)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
