@@ -197,6 +197,14 @@ class ColPml:
         return cls(h)
 
     @classmethod
+    def from_device_rows(cls, ptr: int, r: int, bwt_r: int, n: int, devices=None) -> "ColPml":
+        """Same as from_rows with the 18-byte rows already in GPU memory (`ptr` = device address of r * 18 bytes)."""
+        arr, k = _dev_array(devices)
+        h = C.c_void_p()
+        _check(_L.colbwt_index_from_rows(C.c_void_p(ptr), bwt_r, n, r, arr, k, C.byref(h)), "colbwt_index_from_rows")
+        return cls(h)
+
+    @classmethod
     def from_primaries(cls, prefix: str, devices=None) -> "ColPml":
         """col_pml(heads, lengths, col_ids, thresholds, splits) (col_bwt.hpp:391-395) built on the GPU from
         PREFIX.{bwt.heads,bwt.len,thr_pos,col_runs,col_ids} -- what src/build_col_bwt.cpp does on the CPU."""

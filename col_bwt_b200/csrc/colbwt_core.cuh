@@ -102,9 +102,24 @@ constexpr uint32_t BUILD_FLAG_SLOW = 2u;      // some (row, character) needs the
 constexpr uint32_t BUILD_FLAG_BAD_LF = 4u;    // dest >= r
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+// Flavour of the row gather (development knob; 0 is what ships unless a measurement says otherwise):
+//   0 ld.global.nc (LDG.E.128.CONSTANT, allocates in the L1)   1 ld.global.cg (L2 only)
+//   2 ld.global.nc.L1::no_allocate                               3 ld.global.L1::no_allocate
+#ifndef COLBWT_ROW_LOAD
+#define COLBWT_ROW_LOAD 0
+#endif
 CB_HD Row ld_row(const Row *p)
 {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));   // LDG.E.128.CONSTANT: one 128-bit read-only gather
+    uint4 v;
+#if COLBWT_ROW_LOAD == 1
+    v = __ldcg(reinterpret_cast<const uint4 *>(p));
+#elif COLBWT_ROW_LOAD == 2
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#elif COLBWT_ROW_LOAD == 3
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
+    v = __ldg(reinterpret_cast<const uint4 *>(p));   // LDG.E.128.CONSTANT: one 128-bit read-only gather
+#endif
     return Row{v.x, v.y, v.z, v.w};
 }
 CB_HD uint64_t ld_row64(const uint64_t *p) { return __ldg(reinterpret_cast<const unsigned long long *>(p)); }

@@ -254,10 +254,33 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
         CB_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
     }
     int rc = COLBWT_OK;
+    // rows already in device memory (a table produced on the GPU, e.g. by a build tool): no host hop -- unpack in place
+    // when they sit on this device, device-to-device copy into the staging buffer otherwise
+    bool rows_on_device = false, rows_on_this_device = false;
+    if (rows_host) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, rows_host) == cudaSuccess && pa.type == cudaMemoryTypeDevice) {
+            rows_on_device = true;
+            rows_on_this_device = pa.device == device;
+        }
+        cudaGetLastError();
+    }
     for (uint64_t first = 0, c = 0; first < r; first += chunk_rows, ++c) {
         const int s = (int)(c & 1);
         const uint64_t count = std::min<uint64_t>(chunk_rows, r - first);
         CB_CUDA(cudaEventSynchronize(done[s]));   // staging buffer s free again
+        if (rows_on_device) {
+            const uint8_t *src = (const uint8_t *)rows_host + first * REF_ROW_BYTES;
+            if (!rows_on_this_device) {
+                CB_CUDA(cudaMemcpyAsync(d_stage[s], src, count * REF_ROW_BYTES, cudaMemcpyDefault, sc.streams[s]));
+                src = d_stage[s];
+            }
+            k_unpack_rows<<<(unsigned)((count + 255) / 256), 256, 0, sc.streams[s]>>>(
+                src, first, (uint32_t)count, (uint8_t *)dt.d_ch8, (uint64_t *)dt.d_idx, (uint64_t *)dt.d_thr, d_dest, d_doff, d_cid);
+            CB_CUDA(cudaGetLastError());
+            CB_CUDA(cudaEventRecord(done[s], sc.streams[s]));
+            continue;
+        }
         if (rows_host) {
             memcpy(h_stage[s], (const uint8_t *)rows_host + first * REF_ROW_BYTES, count * REF_ROW_BYTES);
         } else if (fread(h_stage[s], REF_ROW_BYTES, count, fp) != count) {

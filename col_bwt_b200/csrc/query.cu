@@ -930,7 +930,10 @@ static void feed_device(QueryJob &J, int d)
         return;
     }
     Slot *slots = &J.pl->slots[(size_t)d * SLOTS_PER_DEVICE];
-    Slot *prev = nullptr;
+    // Compact forms: the values of a chunk are requested VALUES_LAG chunks after it was enqueued, so that waiting for its
+    // fixed part (= for its kernel) never leaves the GPU without queued work; measured on C2 with a lag of 1: the feeder and
+    // the GPU took turns (52 ms per 1.5 Gbases against 30 ms of kernels).
+    const uint64_t VALUES_LAG = (uint64_t)std::max(1, std::min(3, SLOTS_PER_DEVICE - 2));
     int rc = COLBWT_OK;
     for (uint64_t local = 0; rc == COLBWT_OK && J.rc.load() == COLBWT_OK; ++local) {
         const size_t ci = J.next_chunk.fetch_add(1);
@@ -938,8 +941,11 @@ static void feed_device(QueryJob &J, int d)
         Slot &k = slots[local % (uint64_t)SLOTS_PER_DEVICE];
         if ((rc = drain(J, k, tm)) != COLBWT_OK) break;
         if ((rc = enqueue_chunk(J, d, k, ci, tm)) != COLBWT_OK) break;
-        if (prev && prev != &k) rc = finish_values(J, *prev);   // one chunk behind: the GPU always has the next one queued
-        prev = &k;
+        if (local >= VALUES_LAG) {
+            const double t0 = now_s();
+            rc = finish_values(J, slots[(local - VALUES_LAG) % (uint64_t)SLOTS_PER_DEVICE]);
+            tm.wait += now_s() - t0;
+        }
         ++tm.chunks;
     }
     tm.loop = now_s() - t_begin;
@@ -1012,7 +1018,9 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     Pipeline *plp = nullptr;
     const bool staged_out = pageable_out && kind == OUT_DENSE;
     const Pipeline *before = idx->pipeline;
-    if (int rc = get_pipeline(idx, geo.chunk_reads, geo.chunk_bases, pml_width, staged_out, kind != OUT_DENSE, &plp)) return rc;
+    // compact buffers are allocated as soon as a call could use them, so that trying that mode later does not reallocate
+    const bool want_compact = kind != OUT_DENSE || (allowed & 0xCu) != 0;
+    if (int rc = get_pipeline(idx, geo.chunk_reads, geo.chunk_bases, pml_width, staged_out, want_compact, &plp)) return rc;
     const bool fresh_pipeline = plp != before;   // this call pays for the staging allocations: not a timing sample
 
     QueryJob J;

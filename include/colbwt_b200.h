@@ -78,7 +78,8 @@ typedef struct colbwt_stats {
  * ordinal; devices == NULL means 0..n_devices-1). */
 int colbwt_index_load(const char *path, const int *devices, int n_devices, colbwt_index **out);
 
-/* Same from memory: `rows` = r packed 18-byte col_thr rows exactly as they sit in the file. */
+/* Same from memory: `rows` = r packed 18-byte col_thr rows exactly as they sit in the file.  `rows` may be host memory or
+ * device memory (a table produced on a GPU): device rows are unpacked without a host hop. */
 int colbwt_index_from_rows(const void *rows, uint64_t bwt_r, uint64_t n, uint64_t r,
                            const int *devices, int n_devices, colbwt_index **out);
 

@@ -64,12 +64,15 @@ def write_reference_inputs(prefix: str, idx: dict) -> None:
     formats.write_col_mums(prefix + ".col_mums", idx["num_docs"], idx["mum_len"], idx["mum_pos"])
 
 
-def synth_move_table(r: int, *, mean_len: float = 16.0, mark_frac: float = 0.08, seed: int = 5, device="cuda"):
+def synth_move_table(r: int, *, mean_len: float = 16.0, mark_frac: float = 0.08, seed: int = 5, device="cuda", snap: float = 0.0):
     """Directly synthesised valid move table with r rows (BASELINE configs[4]: index scaled to an HPRC-like run count
     without building a text): random run characters (adjacent runs differ) and lengths, LF columns from the stable
     character sort exactly as LF_table::compute_table derives them, thresholds uniform in the legal gap
-    (end of previous run of the character, start of this run], random chain ids on a fraction of the rows, and one
-    terminator row.  Returns (rows_u8 [r,18] torch tensor on `device` in the `.col_pml` row layout, n, dict of
+    (end of previous run of the character, start of this run] -- or, with probability `snap`, on a run START inside
+    that gap, which is where a real index keeps most of them: the minimum LCP of the gap usually sits where the BWT
+    character changes (0.854 of the thresholds of a 16-haplotype tree-structured pangenome built by this package,
+    profiles/r2/threshold_fit.log); uniform thresholds put two distinct in-row flip offsets on 19 % of the rows, a real
+    table on ~0.01 % -- random chain ids on a fraction of the rows, and one terminator row.  Returns (rows_u8 [r,18] torch tensor on `device` in the `.col_pml` row layout, n, dict of
     LF columns for walking).  Everything stays on `device`."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -108,6 +111,14 @@ def synth_move_table(r: int, *, mean_len: float = 16.0, mark_frac: float = 0.08,
     hi = idx[order]                                   # start of this run
     uu = torch.rand(r, generator=g, device=dev, dtype=torch.float64)
     t = lo + torch.floor(uu * (hi - lo + 1).to(torch.float64)).to(torch.int64)
+    if snap > 0:
+        # a run start inside the gap: the rows after the previous run of the character up to this run are prev+1 .. order
+        u2 = torch.rand(r, generator=g, device=dev, dtype=torch.float64)
+        j = prev + 1 + torch.floor(u2 * (order - prev).clamp(min=1).to(torch.float64)).to(torch.int64)
+        j = torch.minimum(j.clamp(min=0), order)
+        on_start = torch.rand(r, generator=g, device=dev) < snap
+        t = torch.where(on_start & same, idx[j], t)
+        del u2, j, on_start
     thr = torch.zeros(r, dtype=torch.int64, device=dev)
     thr[order] = torch.where(same, t, torch.zeros_like(t))
     del chs, prev, same, lo, hi, uu, t, order

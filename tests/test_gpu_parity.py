@@ -616,3 +616,26 @@ def test_two_replicas_on_one_gpu_feeder_threads(cb, small_index, monkeypatch, co
     res = tbl.query_compact(seqs, off)
     pml, cid = cb.compact_expand(res, off, cb.PML_U16)
     assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_fitted_synthetic_table_from_device_rows(cb):
+    """configs[4] as bench.py builds it: thresholds snapped to run starts like a real index (few exact-search rows), the
+    18-byte rows handed over in GPU memory (colbwt_index_from_rows with a device pointer), mixed short and long walks."""
+    import torch
+    rows, n, cols = PL.synth_move_table(300000, mean_len=16, device="cuda", seed=4, snap=0.854)
+    torch.cuda.synchronize()
+    s1, o1 = PL.walk_reads(cols, 2000, 150, sub=0.01, seed=7)
+    s2, o2 = PL.walk_reads(cols, 6, 9000, sub=0.05, seed=8)
+    seqs = np.concatenate([s1, s2])
+    off = np.concatenate([o1, o2[1:] + o1[-1]]).astype(np.uint64)
+    raw = rows.cpu().numpy()
+    r = np.frombuffer(raw.tobytes(), dtype=F.ROW_DTYPE)
+    cd = {"ch": r["ch"], "idx": F.u40_unpack(r["idx"]), "interval": r["interval"], "offset": r["offset"], "col_id": r["col_id"],
+          "thr": F.u40_unpack(r["thr"]), "n": n, "bwt_r": len(r)}
+    want_p, want_c = oracle.Oracle(columns=cd).query_batch(seqs, off)
+    tbl = cb.ColPml.from_device_rows(rows.data_ptr(), len(r), len(r), n)
+    t_host = cb.ColPml.from_rows(raw, len(r), n)
+    assert tbl.stats.slow_rows == t_host.stats.slow_rows
+    assert tbl.stats.slow_rows < 0.03 * len(r)          # uniform thresholds: ~19 % of the rows
+    pml, cid = tbl.query(seqs, off, cb.PML_U16)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
