@@ -43,6 +43,9 @@ WORKLOADS = {
     "c2small": dict(H=32, G=1_000_000, snp=9e-4, indel=1e-4, reads=2_000_000, read_len=150, sub=0.01, ins=0.0, dele=0.0, len_sigma=0.0, tree=False),
     "c3small": dict(H=64, G=5_000_000, snp=1e-3, indel=1e-4, reads=400_000, read_len=10_000, sub=0.02, ins=0.015, dele=0.015, len_sigma=0.5, tree=True),
 }
+# configs[2] as near its stated size as the tooling's GPU suffix sorter allows (ranks are packed in 31 bits and the working set must fit 180 GB
+# of HBM): 64 haplotypes x 12 Mbp (+ reverse complements: n = 1.54e9); 125 k reads of ~10 kbp per GPU = the stated 1 M reads on 8 GPUs
+WORKLOADS["c3"] = dict(WORKLOADS["c3small"], G=12_000_000, reads=125_000)
 for _s in (1, 100):   # configs[3]: sub-sample sweep on the 32-haplotype index (tunnel marking; `all` mode is covered by golden fixtures)
     WORKLOADS[f"c4_s{_s}"] = dict(WORKLOADS["c2"], split_rate=_s)
 for _s in (1, 10, 100):   # non-tunnel marking: marks come from the product's own GPU col_split (-m all), table from from_primaries
@@ -67,6 +70,7 @@ WORKLOAD_TEXT = {
     "c1": "configs[0]: 4-haplotype x 1 Mbp pangenome (+revcomp), tunnels -s 10, 100k x 150 bp reads",
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
     "c2small": "configs[1] scaled down 10x in genome length and 5x in reads (smoke runs only)",
+    "c3": "configs[2]: 64-haplotype x 12 Mbp tree-structured pangenome (+revcomp, n = 1.54e9: the largest the tooling's GPU suffix sorter fits in 180 GB; stated 50 Mbp), per GPU 125k x ~10 kbp (log-normal) nanopore-like reads at 5% error = the stated 1M reads on 8 GPUs",
     "c3small": "configs[2] scaled down: 64-haplotype x 5 Mbp tree-structured pangenome, 400k x 10 kbp (log-normal lengths) nanopore-like reads at 5% error",
 }
 

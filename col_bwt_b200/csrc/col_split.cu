@@ -4,24 +4,27 @@
 //   FL_table(heads, lengths) / compute_table      FL_table.hpp:86-131, 343-379   -> build_fl_table (stable radix sort by
 //                                                                                    character + scans + binary search)
 //   col_split::split, FL_loop, FL_range           col_split.hpp:54-136, 226-247  -> frontier kernels below
-//   col_split::find_col_runs                      col_split.hpp:258-338          -> resolve_marks (host, sequential sweep)
+//   col_split::find_col_runs                      col_split.hpp:258-338          -> resolve_marks_device (sorts + prefix sums)
 //   col_split::save / serialize_col_runs          col_split.hpp:138-157, 374-390 -> write_outputs
 //
 // The reference walks every multi-MUM forward through the text with FL steps and, every `split_rate` columns, marks
 // the BWT range that the MUM's N suffixes occupy.  All MUMs are independent, so the walk is done level by level on
-// the GPU: a *frontier* holds the current ranges of every MUM still alive; one kernel launch = one FL step of all of
-// them (a range that straddles F-runs falls into pieces; in tunnel mode that ends the MUM, col_split.hpp:81,101).
-// The marks are sorted into the reference's visiting order (MUM, column) and resolved on the host exactly as
-// find_col_runs does (a priority-queue sweep over at most a few million marks).
+// the GPU: a *frontier* holds the current ranges of every MUM still alive; one level = one FL step of all of them (a
+// range that straddles F-runs falls into pieces; in tunnel mode that ends the MUM, col_split.hpp:81,101), and all levels
+// run inside ONE cooperative launch with a grid-wide barrier between them.  The marks are then reduced to one per start
+// and resolved against each other and against the BWT run heads by sorting and prefix sums on the device -- the open-range
+// counts of a sweep decide everything the reference's priority queue decides (see resolve_marks_device).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstring>
-#include <queue>
 #include <string>
 
 #include "internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace colbwt {
 
@@ -38,6 +41,8 @@ struct Range {              // one piece of a MUM's current BWT range
     uint64_t offset;
     uint32_t height, pad;
 };
+
+static_assert(sizeof(Range) == 24, "k_frontier_walk reads a Range as three 64-bit words");
 
 struct Mark {
     uint64_t start;
@@ -139,22 +144,6 @@ __global__ void k_init_frontier(FlTable t, const uint64_t *__restrict__ mum_pos,
     expand(t, r, out, n_out, tunnels != 0);
 }
 
-// One level of FL_loop (col_split.hpp:77-101): column j of every live range.
-__global__ void k_frontier_step(FlTable t, const Range *__restrict__ cur, unsigned long long n_cur, const uint64_t *__restrict__ mum_len,
-                                uint32_t j, uint32_t split_rate, Range *next, unsigned long long *n_next, Mark *marks,
-                                unsigned long long *n_marks, int tunnels)
-{
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cur) return;
-    const Range r = cur[i];
-    if ((uint64_t)j >= mum_len[r.mum]) return;          // this MUM has been walked to its end
-    if (j % split_rate == 0) {
-        const unsigned long long k = atomicAdd(n_marks, 1ull);
-        marks[k] = Mark{t.idx[r.interval] + r.offset, r.mum, j, r.height, 0};
-    }
-    if ((uint64_t)j + 1 < mum_len[r.mum]) expand(t, r, next, n_next, tunnels != 0);
-}
-
 namespace {
 struct DevFree {
     std::vector<void *> p;
@@ -166,77 +155,292 @@ struct DevFree {
         return e;
     }
 };
-
-inline uint32_t bin_id(uint64_t id) { return id >= 256 ? (uint32_t)(id % 255) + 1 : (uint32_t)id; }   // col_split.hpp:222-224
 } // namespace
 
-// find_col_runs (col_split.hpp:258-338) on the marks in visiting order.  Returns set bits of col_runs + id per bit.
-static void resolve_marks(uint64_t n, const std::vector<uint64_t> &run_starts, std::vector<Mark> &marks, bool mode_all,
-                          std::vector<uint64_t> &out_pos, std::vector<uint8_t> &out_id)
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole FL walk as ONE cooperative launch: every level of FL_loop (col_split.hpp:77-101) is a grid-stride pass over the
+// live ranges followed by a grid-wide barrier, so the host neither launches per column nor reads a counter back (multi-MUMs
+// are 1e5-1e6 columns long on a real pangenome).  counts[0..2] rotate as (current, next, to be zeroed); counts[3] = marks.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_frontier_walk(FlTable t, Range *buf_a, Range *buf_b, const uint64_t *__restrict__ mum_len, uint32_t max_len,
+                                                        uint32_t split_rate, Mark *marks, unsigned long long *counts, unsigned long long cap_ranges,
+                                                        unsigned long long cap_marks, int tunnels, unsigned int *status)
 {
-    // second pass of split(): one (id, height) per distinct start (collect_ids, col_split.hpp:114-127)
-    std::stable_sort(marks.begin(), marks.end(), [](const Mark &a, const Mark &b) { return a.mum != b.mum ? a.mum < b.mum : a.col < b.col; });
-    struct Slot { uint64_t start; uint32_t id, height; uint64_t seq; };
-    std::vector<Slot> slots(marks.size());
-    for (size_t i = 0; i < marks.size(); ++i) slots[i] = Slot{marks[i].start, bin_id((uint64_t)marks[i].mum + 1), marks[i].height, i};
-    std::stable_sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) { return a.start != b.start ? a.start < b.start : a.seq < b.seq; });
-    std::vector<Slot> uniq;
-    for (size_t i = 0; i < slots.size();) {
-        size_t e = i;
-        uint32_t id = 0, h = 0;
-        for (; e < slots.size() && slots[e].start == slots[i].start; ++e) {
-            if (mode_all) {                     // keep the taller one; on ties the one visited first
-                if (!(h >= slots[e].height)) id = slots[e].id;
-                h = std::max(h, slots[e].height);
-            } else {                            // tunnel mode: the last visit wins
-                id = slots[e].id;
-                h = slots[e].height;
+    cg::grid_group grid = cg::this_grid();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Range *cur = buf_a, *next = buf_b;
+    for (uint32_t j = 0; j < max_len; ++j) {
+        // counters and ranges are written by other SMs one level earlier and were read here two or three levels ago: read them
+        // past the L1 (ld.global.cg), which a grid-wide barrier does not invalidate
+        const unsigned long long n_cur = __ldcg(counts + j % 3);
+        if (n_cur == 0) break;                                   // same value for every thread: read after the barrier below
+        if (n_cur > cap_ranges || __ldcg(counts + 3) > cap_marks) {       // cannot happen (the capacities are true upper bounds); never write past them
+            if (tid == 0) *status = 1;
+            break;
+        }
+        if (tid == 0) counts[(j + 2) % 3] = 0;                   // last read one level ago, written again one level from now
+        unsigned long long *n_next = counts + (j + 1) % 3;
+        for (unsigned long long i = tid; i < n_cur; i += stride) {
+            const unsigned long long *rp = reinterpret_cast<const unsigned long long *>(cur + i);
+            const unsigned long long w0 = __ldcg(rp), w1 = __ldcg(rp + 1), w2 = __ldcg(rp + 2);
+            Range r;
+            r.mum = (uint32_t)w0;
+            r.interval = (uint32_t)(w0 >> 32);
+            r.offset = w1;
+            r.height = (uint32_t)w2;
+            r.pad = (uint32_t)(w2 >> 32);
+            if ((uint64_t)j >= mum_len[r.mum]) continue;         // this MUM has been walked to its end
+            if (j % split_rate == 0) {
+                const unsigned long long k = atomicAdd(counts + 3, 1ull);
+                if (k < cap_marks) marks[k] = Mark{t.idx[r.interval] + r.offset, r.mum, j, r.height, 0};
             }
+            if ((uint64_t)j + 1 < mum_len[r.mum]) expand(t, r, next, n_next, tunnels != 0);
         }
-        uniq.push_back(Slot{slots[i].start, id, h, 0});
-        i = e;
+        grid.sync();
+        Range *tmp = cur;
+        cur = next;
+        next = tmp;
     }
-    // sweep
-    struct Open { uint64_t end, start; uint32_t id; };
-    auto later = [](const Open &a, const Open &b) { return a.end != b.end ? a.end > b.end : a.start > b.start; };
-    std::priority_queue<Open, std::vector<Open>, decltype(later)> open(later);
-    size_t run_cursor = 0;                      // next BWT run head not yet emitted
-    uint32_t last_id = 0;
-    auto update_bwt_pos = [&](uint64_t idx, uint32_t id) {
-        while (run_cursor < run_starts.size() && run_starts[run_cursor] < idx) {
-            out_pos.push_back(run_starts[run_cursor]);
-            out_id.push_back((uint8_t)last_id);
-            ++run_cursor;
-        }
-        if (run_cursor < run_starts.size() && run_starts[run_cursor] == idx) ++run_cursor;
-        last_id = id;
-    };
-    auto update_col_ranges = [&](uint64_t idx) {
-        while (!open.empty() && open.top().end <= idx) {
-            const Open e = open.top();
-            open.pop();
-            if (open.size() == 1 && open.top().end > e.end) {
-                update_bwt_pos(e.end, open.top().id);
-                out_pos.push_back(e.end);
-                out_id.push_back((uint8_t)open.top().id);
-            } else if (open.empty() && e.end < idx) {
-                update_bwt_pos(e.end, 0);
-                out_pos.push_back(e.end);
-                out_id.push_back(0);
-            }
-        }
-    };
-    for (const Slot &s : uniq) {
-        update_col_ranges(s.start);
-        open.push(Open{s.start + s.height, s.start, s.id});
-        if (open.size() == 1 && s.id > 0) {
-            update_bwt_pos(s.start, s.id);
-            out_pos.push_back(s.start);
-            out_id.push_back((uint8_t)s.id);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Overlap resolution (col_split.hpp:105-132 second pass + find_col_runs :258-338) as sorts and scans.
+//
+// What the reference's priority-queue sweep emits depends only on how many marked ranges are open around each event of a
+// sweep over the range starts and ends (ends before starts at equal positions, ends ordered by (end, start)):
+//   * a range that starts while none is open begins a sub-run with its id;
+//   * a range that ends leaving exactly ONE open (which ends later) hands the position to that one: sub-run with ITS id;
+//   * a range that ends leaving none open begins an unmarked sub-run (id 0), unless another range starts right there or
+//     the position is n;
+//   * BWT run heads that are none of these positions become sub-runs carrying the id in force (that of the last such
+//     boundary before them, 0 if none).
+// The number of open ranges is a prefix sum of +1/-1 over the sorted events; WHICH range is the one left open is the
+// prefix sum of +/-(index+1), read where the count is 1.  No queue, no sequential state.
+// ---------------------------------------------------------------------------------------------------------------------
+struct UniqueMark { uint64_t start, end; uint32_t id, pad; };
+
+__device__ __forceinline__ uint32_t bin_id_dev(uint64_t id) { return id >= 256 ? (uint32_t)(id % 255) + 1 : (uint32_t)id; }   // col_split.hpp:222-224
+
+__global__ void k_mark_keys(const Mark *__restrict__ marks, uint64_t n_marks, uint64_t *visit_key, uint32_t *iota)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_marks) return;
+    visit_key[i] = ((uint64_t)marks[i].mum << 32) | marks[i].col;   // the reference's visiting order: MUM, then column
+    iota[i] = (uint32_t)i;
+}
+
+__global__ void k_start_keys(const Mark *__restrict__ marks, const uint32_t *__restrict__ by_visit, uint64_t n_marks, uint64_t *start_key)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_marks) start_key[i] = marks[by_visit[i]].start;
+}
+
+__global__ void k_segment_heads(const uint64_t *__restrict__ start_sorted, uint64_t n_marks, uint32_t *is_head)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_marks) is_head[i] = (i == 0 || start_sorted[i] != start_sorted[i - 1]) ? 1u : 0u;
+}
+
+// One thread per distinct start: marks with that start are consecutive and in visiting order (collect_ids, col_split.hpp:114-127).
+__global__ void k_unique_marks(const Mark *__restrict__ marks, const uint32_t *__restrict__ order, const uint64_t *__restrict__ start_sorted,
+                               const uint32_t *__restrict__ is_head, const uint32_t *__restrict__ head_rank, uint64_t n_marks, int mode_all, UniqueMark *out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_marks || !is_head[i]) return;
+    uint32_t id = 0, h = 0;
+    for (uint64_t e = i; e < n_marks && start_sorted[e] == start_sorted[i]; ++e) {
+        const Mark m = marks[order[e]];
+        const uint32_t mid = bin_id_dev((uint64_t)m.mum + 1);
+        if (mode_all) {                     // the taller range wins; on ties the one visited first
+            if (!(h >= m.height)) id = mid;
+            h = max(h, m.height);
+        } else {                            // tunnel mode: the last visit wins
+            id = mid;
+            h = m.height;
         }
     }
-    update_col_ranges(n);
-    update_bwt_pos(n, 0);
+    out[head_rank[i]] = UniqueMark{start_sorted[i], start_sorted[i] + h, id, 0};
+}
+
+__global__ void k_event_keys(const UniqueMark *__restrict__ u, uint64_t m, uint64_t *key, uint32_t *payload)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    key[i] = u[i].end << 1;                 // ends first at equal positions; ends keep their start order (stable sort)
+    payload[i] = (uint32_t)i;
+    key[m + i] = (u[i].start << 1) | 1;
+    payload[m + i] = (uint32_t)i;
+}
+
+__global__ void k_event_deltas(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, uint64_t n_events, long long *d_count, long long *d_sum)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_events) return;
+    const long long sign = (key[i] & 1) ? 1 : -1;
+    d_count[i] = sign;
+    d_sum[i] = sign * ((long long)payload[i] + 1);
+}
+
+__global__ void k_event_flags(const uint64_t *__restrict__ key, const uint32_t *__restrict__ payload, const long long *__restrict__ count,
+                              const long long *__restrict__ sum, const UniqueMark *__restrict__ u, uint64_t n_events, uint64_t n, uint32_t *flag, uint32_t *id_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_events) return;
+    const uint64_t pos = key[i] >> 1;
+    uint32_t f = 0, id = 0;
+    if (key[i] & 1) {                                           // a range starts
+        if (count[i] == 1) { f = 1; id = u[payload[i]].id; }    // nothing else open
+    } else if (count[i] == 1) {                                 // a range ends and exactly one stays open
+        const UniqueMark &left = u[sum[i] - 1];
+        if (left.end > pos) { f = 1; id = left.id; }
+    } else if (count[i] == 0) {                                 // a range ends and nothing stays open
+        const bool start_here = i + 1 < n_events && key[i + 1] == ((pos << 1) | 1);
+        if (!start_here && pos < n) f = 1;
+    }
+    flag[i] = f;
+    id_out[i] = id;
+}
+
+__global__ void k_compact_boundaries(const uint64_t *__restrict__ key, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank,
+                                     const uint32_t *__restrict__ id_in, uint64_t n_events, uint64_t *b_pos, uint8_t *b_id, unsigned long long *bits)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_events || !flag[i]) return;
+    const uint64_t pos = key[i] >> 1;
+    b_pos[rank[i]] = pos;
+    b_id[rank[i]] = (uint8_t)id_in[i];
+    atomicOr(bits + (pos >> 6), 1ull << (pos & 63));
+}
+
+__global__ void k_set_head_bits(const uint64_t *__restrict__ run_start, uint64_t runs, unsigned long long *bits)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < runs) atomicOr(bits + (run_start[i] >> 6), 1ull << (run_start[i] & 63));
+}
+
+__global__ void k_popc_words(const unsigned long long *__restrict__ bits, uint64_t nw, uint64_t *cnt)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) cnt[i] = (uint64_t)__popcll(bits[i]);
+}
+
+__device__ __forceinline__ uint64_t bit_rank(const unsigned long long *bits, const uint64_t *prefix, uint64_t pos)
+{
+    return prefix[pos >> 6] + (uint64_t)__popcll(bits[pos >> 6] & ((1ull << (pos & 63)) - 1ull));
+}
+
+// Run heads: id in force = id of the last boundary before the head; a head that is itself a boundary is written by k_boundary_ids.
+__global__ void k_head_ids(const uint64_t *__restrict__ run_start, uint64_t runs, const uint64_t *__restrict__ b_pos, const uint8_t *__restrict__ b_id,
+                           uint64_t n_b, const unsigned long long *__restrict__ bits, const uint64_t *__restrict__ prefix, uint8_t *ids)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= runs) return;
+    const uint64_t p = run_start[i];
+    uint64_t lo = 0, hi = n_b;                  // first boundary at or after p
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (b_pos[mid] < p) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_b && b_pos[lo] == p) return;
+    ids[bit_rank(bits, prefix, p)] = lo ? b_id[lo - 1] : 0;
+}
+
+__global__ void k_boundary_ids(const uint64_t *__restrict__ b_pos, const uint8_t *__restrict__ b_id, uint64_t n_b, const unsigned long long *__restrict__ bits,
+                               const uint64_t *__restrict__ prefix, uint8_t *ids)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_b) ids[bit_rank(bits, prefix, b_pos[i])] = b_id[i];
+}
+
+// marks (device, any order) -> words of the col_runs bit vector + one id per set bit, both on the host.
+static int resolve_marks_device(DevFree &mem, const Mark *d_marks, uint64_t n_marks, const uint64_t *d_run_start, uint64_t runs, uint64_t n, bool mode_all,
+                                std::vector<uint64_t> &words, std::vector<uint8_t> &ids)
+{
+    auto grid = [](uint64_t k) { return (unsigned)((k + 255) / 256); };
+    // ---- one (id, height) per distinct start: sort by visit, then stably by start -----------------------------------------
+    uint64_t *d_k1, *d_k2;
+    uint32_t *d_v1, *d_v2, *d_head, *d_head_rank;
+    CB_CUDA(mem.alloc(&d_k1, 2 * n_marks));
+    CB_CUDA(mem.alloc(&d_k2, 2 * n_marks));
+    CB_CUDA(mem.alloc(&d_v1, 2 * n_marks));
+    CB_CUDA(mem.alloc(&d_v2, 2 * n_marks));
+    CB_CUDA(mem.alloc(&d_head, 2 * n_marks));
+    CB_CUDA(mem.alloc(&d_head_rank, 2 * n_marks + 1));
+    size_t tb = 0, tb2 = 0, tb3 = 0;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t *)d_k1, d_k2, (const uint32_t *)d_v1, d_v2, (int64_t)(2 * n_marks), 0, 64));
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, (const uint32_t *)d_head, d_head_rank, (int64_t)(2 * n_marks + 1)));
+    CB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb3, (const long long *)nullptr, (long long *)nullptr, (int64_t)(2 * n_marks)));
+    const uint64_t nw = (n + 63) / 64;
+    size_t tb4 = 0;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb4, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)nw));
+    const size_t temp_bytes = std::max(std::max(tb, tb2), std::max(tb3, tb4)) + 256;
+    uint8_t *d_temp;
+    CB_CUDA(mem.alloc(&d_temp, temp_bytes));
+    k_mark_keys<<<grid(n_marks), 256>>>(d_marks, n_marks, d_k1, d_v1);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint64_t *)d_k1, d_k2, (const uint32_t *)d_v1, d_v2, (int64_t)n_marks, 0, 64));
+    k_start_keys<<<grid(n_marks), 256>>>(d_marks, d_v2, n_marks, d_k1);                 // d_v2 = marks in visiting order
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint64_t *)d_k1, d_k2, (const uint32_t *)d_v2, d_v1, (int64_t)n_marks, 0, 40));
+    // now d_k2 = starts ascending, d_v1 = mark index; equal starts in visiting order (the sort is stable)
+    k_segment_heads<<<grid(n_marks), 256>>>(d_k2, n_marks, d_head);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, tb, (const uint32_t *)d_head, d_head_rank, (int64_t)(n_marks + 1)));
+    uint32_t m32 = 0;
+    CB_CUDA(cudaMemcpy(&m32, d_head_rank + n_marks, 4, cudaMemcpyDeviceToHost));
+    const uint64_t m = m32;
+    UniqueMark *d_u;
+    CB_CUDA(mem.alloc(&d_u, m));
+    k_unique_marks<<<grid(n_marks), 256>>>(d_marks, d_v1, d_k2, d_head, d_head_rank, n_marks, mode_all ? 1 : 0, d_u);
+    // ---- the sweep as a sort of 2m events and two prefix sums -----------------------------------------------------------
+    const uint64_t n_events = 2 * m;
+    long long *d_dc, *d_ds;
+    uint32_t *d_flag = d_head, *d_rank = d_head_rank, *d_eid;
+    CB_CUDA(mem.alloc(&d_dc, n_events));
+    CB_CUDA(mem.alloc(&d_ds, n_events));
+    CB_CUDA(mem.alloc(&d_eid, n_events));
+    k_event_keys<<<grid(m), 256>>>(d_u, m, d_k1, d_v1);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint64_t *)d_k1, d_k2, (const uint32_t *)d_v1, d_v2, (int64_t)n_events, 0, 42));
+    k_event_deltas<<<grid(n_events), 256>>>(d_k2, d_v2, n_events, d_dc, d_ds);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceScan::InclusiveSum(d_temp, tb, (const long long *)d_dc, d_dc, (int64_t)n_events));
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceScan::InclusiveSum(d_temp, tb, (const long long *)d_ds, d_ds, (int64_t)n_events));
+    k_event_flags<<<grid(n_events), 256>>>(d_k2, d_v2, d_dc, d_ds, d_u, n_events, n, d_flag, d_eid);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, tb, (const uint32_t *)d_flag, d_rank, (int64_t)(n_events + 1)));
+    uint32_t nb32 = 0;
+    CB_CUDA(cudaMemcpy(&nb32, d_rank + n_events, 4, cudaMemcpyDeviceToHost));
+    const uint64_t n_b = nb32;
+    // ---- boundaries + run heads -> bit vector, ranks, ids ------------------------------------------------------------------
+    uint64_t *d_bpos, *d_cnt, *d_prefix;
+    uint8_t *d_bid, *d_ids;
+    unsigned long long *d_bits;
+    CB_CUDA(mem.alloc(&d_bpos, n_b));
+    CB_CUDA(mem.alloc(&d_bid, n_b));
+    CB_CUDA(mem.alloc(&d_bits, nw));
+    CB_CUDA(mem.alloc(&d_cnt, nw));
+    CB_CUDA(mem.alloc(&d_prefix, nw));
+    CB_CUDA(cudaMemset(d_bits, 0, nw * 8));
+    k_compact_boundaries<<<grid(n_events), 256>>>(d_k2, d_flag, d_rank, d_eid, n_events, d_bpos, d_bid, d_bits);
+    k_set_head_bits<<<grid(runs), 256>>>(d_run_start, runs, d_bits);
+    k_popc_words<<<grid(nw), 256>>>(d_bits, nw, d_cnt);
+    tb = temp_bytes;
+    CB_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, tb, (const uint64_t *)d_cnt, d_prefix, (int64_t)nw));
+    uint64_t last_pre = 0, last_cnt = 0;
+    CB_CUDA(cudaMemcpy(&last_pre, d_prefix + (nw - 1), 8, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(&last_cnt, d_cnt + (nw - 1), 8, cudaMemcpyDeviceToHost));
+    const uint64_t set_bits = last_pre + last_cnt;
+    CB_CUDA(mem.alloc(&d_ids, set_bits));
+    k_head_ids<<<grid(runs), 256>>>(d_run_start, runs, d_bpos, d_bid, n_b, d_bits, d_prefix, d_ids);
+    k_boundary_ids<<<grid(n_b), 256>>>(d_bpos, d_bid, n_b, d_bits, d_prefix, d_ids);
+    CB_CUDA(cudaGetLastError());
+    words.resize(nw);
+    ids.resize(set_bits);
+    CB_CUDA(cudaMemcpy(words.data(), d_bits, nw * 8, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(ids.data(), d_ids, set_bits, cudaMemcpyDeviceToHost));
+    return COLBWT_OK;
 }
 
 static bool read_all(const std::string &path, std::vector<uint8_t> &out)
@@ -298,6 +502,15 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
         mum_pos[i] = mums[2 + 2 * i];
         max_len = std::max(max_len, mum_len[i]);
     }
+    // The reference consumes the MUM positions with ONE forward cursor over the BWT runs (FL_loop, col_split.hpp:70-100): a
+    // position smaller than its predecessor stalls that cursor and every later MUM is silently dropped.  mumemto writes them
+    // ascending; anything else is refused here rather than reproduced.
+    for (uint32_t i = 1; i < n_mums; ++i)
+        if (mum_pos[i] < mum_pos[i - 1]) {
+            set_error("%s.col_mums: positions must be ascending (entry %u: %llu after %llu)", prefix, i, (unsigned long long)mum_pos[i],
+                      (unsigned long long)mum_pos[i - 1]);
+            return COLBWT_ERR_FORMAT;
+        }
     const uint64_t runs = heads.size();
     std::vector<uint64_t> run_starts(runs);
     uint64_t n = 0;
@@ -365,48 +578,59 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
     const uint64_t cap_marks = total_cols * (mode_all ? num_docs : 1) + 1024;
     Range *d_cur, *d_next;
     Mark *d_marks;
-    unsigned long long *d_counts;   // [0] cur, [1] next, [2] marks
+    unsigned long long *d_counts;   // [0..2] live ranges of three consecutive levels (rotating), [3] marks
+    unsigned int *d_status;
     CB_CUDA(mem.alloc(&d_cur, cap_ranges));
     CB_CUDA(mem.alloc(&d_next, cap_ranges));
     CB_CUDA(mem.alloc(&d_marks, cap_marks));
     CB_CUDA(mem.alloc(&d_counts, 4));
+    CB_CUDA(mem.alloc(&d_status, 1));
     CB_CUDA(cudaMemset(d_counts, 0, 32));
-    if (n_mums) k_init_frontier<<<(n_mums + 255) / 256, 256>>>(t, d_mum_pos, n_mums, num_docs, d_cur, d_counts + 0, !mode_all);
+    CB_CUDA(cudaMemset(d_status, 0, 4));
     unsigned long long h_counts[4] = {0, 0, 0, 0};
-    for (uint32_t j = 0; j < max_len; ++j) {
-        CB_CUDA(cudaMemcpy(h_counts, d_counts, 32, cudaMemcpyDeviceToHost));
-        if (h_counts[0] == 0) break;
-        if (h_counts[0] > cap_ranges || h_counts[2] > cap_marks) {
-            set_error("internal: frontier overflow (%llu ranges, %llu marks)", h_counts[0], h_counts[2]);
-            return COLBWT_ERR_NOMEM;
-        }
-        CB_CUDA(cudaMemset(d_counts + 1, 0, 8));
-        k_frontier_step<<<(unsigned)((h_counts[0] + 255) / 256), 256>>>(t, d_cur, h_counts[0], d_mum_len, j, (uint32_t)split_rate, d_next, d_counts + 1,
-                                                                       d_marks, d_counts + 2, !mode_all);
+    if (n_mums) {
+        k_init_frontier<<<(n_mums + 255) / 256, 256>>>(t, d_mum_pos, n_mums, num_docs, d_cur, d_counts + 0, !mode_all);
         CB_CUDA(cudaGetLastError());
-        CB_CUDA(cudaMemcpy(d_counts + 0, d_counts + 1, 8, cudaMemcpyDeviceToDevice));
-        std::swap(d_cur, d_next);
+        // every level of the walk inside one cooperative launch (grid-wide barrier between levels): no per-column launch,
+        // no counter read back by the host
+        int per_sm = 0, sms = 0, coop = 0;
+        CB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        CB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frontier_walk, 256, 0));
+        if (!coop || per_sm < 1) {
+            set_error("colbwt_col_split: the device cannot run a cooperative launch");
+            return COLBWT_ERR_CUDA;
+        }
+        uint32_t max_len32 = (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFull), rate32 = (uint32_t)split_rate;
+        unsigned long long cap_r = cap_ranges, cap_m = cap_marks;
+        int tunnels = !mode_all;
+        void *args[] = {&t, &d_cur, &d_next, &d_mum_len, &max_len32, &rate32, &d_marks, &d_counts, &cap_r, &cap_m, &tunnels, &d_status};
+        CB_CUDA(cudaLaunchCooperativeKernel((const void *)k_frontier_walk, dim3((unsigned)(sms * std::min(per_sm, 4))), dim3(256), args, 0, nullptr));
+        CB_CUDA(cudaDeviceSynchronize());
     }
+    unsigned int h_status = 0;
+    CB_CUDA(cudaMemcpy(&h_status, d_status, 4, cudaMemcpyDeviceToHost));
     CB_CUDA(cudaMemcpy(h_counts, d_counts, 32, cudaMemcpyDeviceToHost));
-    if (h_counts[2] > cap_marks) {
-        set_error("internal: mark buffer overflow");
+    if (h_status || h_counts[3] > cap_marks) {
+        set_error("internal: frontier overflow (%llu marks of %llu)", h_counts[3], (unsigned long long)cap_marks);
         return COLBWT_ERR_NOMEM;
     }
-    std::vector<Mark> marks(h_counts[2]);
-    CB_CUDA(cudaMemcpy(marks.data(), d_marks, marks.size() * sizeof(Mark), cudaMemcpyDeviceToHost));
+    const uint64_t n_marks = h_counts[3];
 
-    // ---- overlaps + run heads, then the two output files -------------------------------------------------------------
-    std::vector<uint64_t> pos;
+    // ---- overlaps + run heads (on the device), then the two output files -----------------------------------------------------
+    std::vector<uint64_t> words;
     std::vector<uint8_t> ids;
-    if (!marks.empty()) resolve_marks(n, run_starts, marks, mode_all != 0, pos, ids);   // find_col_runs returns early without marks (col_split.hpp:259)
-    std::vector<uint64_t> words((n + 63) / 64, 0);
-    for (uint64_t q : pos) words[q >> 6] |= 1ull << (q & 63);
+    uint64_t n_bits = 0;                         // find_col_runs returns early without marks (col_split.hpp:259): col_runs stays empty
+    if (n_marks) {
+        if (int rc = resolve_marks_device(mem, d_marks, n_marks, d_lstart, runs, n, mode_all != 0, words, ids)) return rc;
+        n_bits = n;
+    }
     FILE *f = fopen((p + ".col_runs").c_str(), "wb");
     if (!f) {
         set_error("cannot write %s.col_runs", prefix);
         return COLBWT_ERR_IO;
     }
-    fwrite(&n, 8, 1, f);                        // sdsl bit_vector: length in bits, then the words (col_split.hpp:384-386)
+    fwrite(&n_bits, 8, 1, f);                   // sdsl bit_vector: length in bits, then the words (col_split.hpp:384-386)
     fwrite(words.data(), 8, words.size(), f);
     fclose(f);
     f = fopen((p + ".col_ids").c_str(), "wb");
@@ -416,7 +640,7 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
     }
     fwrite(ids.data(), 1, ids.size(), f);       // one ID_BYTES = 1 byte per set bit (col_split.hpp:147-155)
     fclose(f);
-    if (n_set_bits) *n_set_bits = pos.size();
+    if (n_set_bits) *n_set_bits = ids.size();
     if (n_marked) {
         uint64_t m = 0;
         for (uint8_t v : ids) m += v != 0;

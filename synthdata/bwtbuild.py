@@ -119,6 +119,49 @@ class SuffixIndex:
         return out
 
 
+def lcp_irreducible(si: "SuffixIndex", bwt: torch.Tensor) -> torch.Tensor:
+    """The same LCP array without the doubling levels (which cost 4 bytes x n x ~14 rounds: the limit on text size).
+
+    LCP[i] is *reducible* when both suffixes are preceded by the same text character (BWT[i] == BWT[i-1]); then
+    PLCP[SA[i]] = PLCP[SA[i]-1] - 1 (Karkkainen, Manzini & Puglisi 2009), so in text order PLCP[j] + j is non-decreasing and
+    constant over reducible positions.  Only the irreducible entries -- about one per BWT run -- are computed, by comparing
+    the packed k-mer keys k symbols at a time; a running maximum in text order gives the rest.  int64, exact."""
+    n, dev, k, bits = si.n, si.sa.device, si.k, si.bits
+    sa = si.sa
+    irr = torch.ones(n, dtype=torch.bool, device=dev)
+    irr[1:] = (bwt[1:] != bwt[:-1]) | (sa[1:] == 0) | (sa[:-1] == 0)
+    pos = torch.nonzero(irr).flatten()
+    pos = pos[pos > 0]
+    a, b = sa[pos], sa[pos - 1]
+    acc = torch.zeros_like(a)
+    alive = torch.arange(a.numel(), device=dev)
+    mask = (1 << bits) - 1
+    while alive.numel():
+        ai = (a[alive] + acc[alive]).clamp(max=n - 1)
+        bi = (b[alive] + acc[alive]).clamp(max=n - 1)
+        x = si.kmer[ai] ^ si.kmer[bi]
+        same = x == 0
+        # a mismatch inside this k-mer: count the matching leading symbols
+        xs = x[~same]
+        rem = torch.zeros_like(xs)
+        going = torch.ones_like(xs, dtype=torch.bool)
+        for j in range(k):
+            going &= ((xs >> ((k - 1 - j) * bits)) & mask) == 0
+            rem += going.to(rem.dtype)
+        acc[alive[~same]] += rem
+        acc[alive[same]] += k
+        alive = alive[same]
+    # text order: A[j] = PLCP[j] + j at irreducible j, running maximum elsewhere (SA row 0 has LCP 0 by definition)
+    A = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    A[a] = acc + a
+    A[sa[0]] = sa[0]
+    del acc, alive, a, b, pos, irr
+    A = torch.cummax(A, 0).values
+    out = A[sa] - sa
+    out[0] = 0
+    return out
+
+
 def bwt_runs(bwt: torch.Tensor):
     """Run-length encode the BWT with terminator bytes (<=1) folded to 1 (col_bwt.hpp:171).
     Returns (heads u8, starts int64, lens int64)."""
@@ -172,6 +215,7 @@ def multi_mums(si: SuffixIndex, lcp: torch.Tensor, bwt: torch.Tensor, seq_starts
     room_prev = torch.zeros_like(room)
     room_prev[1:] = room[:-1]
     l = torch.minimum(lcp, torch.minimum(room, room_prev))
+    del room, room_prev
     # sliding minimum of l over rows i+1 .. i+N-1  (window of N-1 values)
     w = N - 1
     big = torch.iinfo(torch.int64).max
@@ -186,7 +230,11 @@ def multi_mums(si: SuffixIndex, lcp: torch.Tensor, bwt: torch.Tensor, seq_starts
     inner = m[1: n + 1]                      # inner[i] = min l[i+1 .. i+N-1]
     left = l                                 # l[i]   : lcp with the row above the window
     right = lpad[N: n + N]                   # l[i+N] : lcp with the row below the window (0 past the end)
-    cand = torch.nonzero((inner >= min_len) & (left < inner) & (right < inner)).flatten()
+    sel = inner >= min_len
+    sel &= left < inner
+    sel &= right < inner
+    cand = torch.nonzero(sel).flatten()
+    del sel
     cand = cand[cand + N <= n]
     if cand.numel() == 0:
         z = np.zeros(0, dtype=np.uint64)

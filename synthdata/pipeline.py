@@ -22,10 +22,16 @@ def build_index(haps, *, with_revcomp=True, split_rate=10, min_mum=20, device="c
         torch.set_num_threads(1)  # torch's CPU sort is far slower when its threads oversubscribe a small cgroup
     text, seq_starts, doc_of_seq = pangenome.build_text(haps, with_revcomp=with_revcomp)
     num_docs = len(haps)
-    si = bwtbuild.SuffixIndex(text, device=device)
+    # large texts: no doubling levels (4 bytes x n per round), LCP from the irreducible entries instead -- same array
+    big = text.size > 700_000_000
+    si = bwtbuild.SuffixIndex(text, device=device, keep_levels=not big)
     bwt = si.bwt()
-    lcp = si.lcp()
+    lcp = bwtbuild.lcp_irreducible(si, bwt) if big else si.lcp()
     si.levels = []  # free
+    if big:
+        si.kmer = None
+        if str(device) != "cpu":
+            torch.cuda.empty_cache()
     heads, starts, lens = bwtbuild.bwt_runs(bwt)
     thr = bwtbuild.thresholds(bwt, lcp, heads, starts)
     if verbose:

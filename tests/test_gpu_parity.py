@@ -639,3 +639,34 @@ def test_fitted_synthetic_table_from_device_rows(cb):
     assert tbl.stats.slow_rows < 0.03 * len(r)          # uniform thresholds: ~19 % of the rows
     pml, cid = tbl.query(seqs, off, cb.PML_U16)
     assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+def test_col_split_overlapping_marks_against_the_reference_binary(cb, tmp_path):
+    """`-m all` / `-m tunnels` on a small divergent pangenome with many overlapping multi-MUM ranges: the device-side resolution
+    (sorts + prefix sums, col_split.cu) must write, byte for byte, what the reference's priority-queue sweep writes -- the
+    reference's own build_FL + col_split (oracle/_ref, compiled from the reference sources) run on the same inputs."""
+    import shutil
+    if not oracle.have_ref() or not os.path.exists(oracle.ref_bin("col_split")):
+        pytest.skip("oracle/_ref not built")
+    haps = P.make_haplotypes(3000, 5, snp=4e-3, indel=5e-4, seed=21, tree=True)
+    idx = PL.build_index(haps, split_rate=2, min_mum=8)
+    p, q = str(tmp_path / "o.fa"), str(tmp_path / "ref.fa")
+    PL.write_reference_inputs(p, idx)
+    for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".col_mums"):
+        shutil.copy(p + ext, q + ext)
+    subprocess.run([oracle.ref_bin("build_FL"), q], check=True, capture_output=True)
+    for mode, rate in (("all", 1), ("all", 3), ("tunnels", 1), ("tunnels", 7)):
+        subprocess.run([oracle.ref_bin("col_split"), q, "-m", mode, "-s", str(rate)], check=True, capture_output=True)
+        bits, marked = cb.col_split(p, mode, rate)
+        for ext in (".col_runs", ".col_ids"):
+            assert open(p + ext, "rb").read() == open(q + ext, "rb").read(), (mode, rate, ext)
+        ids = np.fromfile(p + ".col_ids", np.uint8)
+        assert bits == ids.size and marked == int((ids > 0).sum()) and marked > 0
+    with open(p + ".col_mums", "rb") as f:
+        raw = bytearray(f.read())
+    assert len(raw) >= 25
+    raw[5:15], raw[15:25] = raw[15:25], raw[5:15]                                   # swap the first two (len, pos) pairs: positions descend
+    open(p + ".col_mums", "wb").write(bytes(raw))
+    with pytest.raises(cb.ColBwtError) as e:
+        cb.col_split(p, "all", 1)
+    assert e.value.code == -2

@@ -69,3 +69,17 @@ def _sa_isa(idx):
     si = B.SuffixIndex(idx["text"], keep_levels=False)
     run_starts = torch.as_tensor(np.cumsum(idx["lens"]) - idx["lens"])
     return si.sa, si.isa, run_starts
+
+
+def test_lcp_from_irreducible_entries_equals_lcp_from_levels():
+    """bwtbuild.lcp_irreducible (used for texts too large to keep the doubling levels) against SuffixIndex.lcp."""
+    import torch
+    from synthdata import bwtbuild
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(3)
+    haps = P.make_haplotypes(4000, 5, snp=2e-3, indel=2e-4, seed=9, tree=True)
+    text, _, _ = P.build_text(haps, with_revcomp=True)
+    cases = [text] + [np.concatenate([rng.choice(np.frombuffer(b"AC\x01", np.uint8), size=int(rng.integers(3, 150))), [0]]).astype(np.uint8) for _ in range(15)]
+    for t in cases:
+        si = bwtbuild.SuffixIndex(t)
+        assert bool((si.lcp() == bwtbuild.lcp_irreducible(si, si.bwt())).all())
