@@ -46,6 +46,7 @@ WORKLOADS = {
 # configs[2] as near its stated size as the tooling's GPU suffix sorter allows (ranks are packed in 31 bits and the working set must fit 180 GB
 # of HBM): 64 haplotypes x 12 Mbp (+ reverse complements: n = 1.54e9); 125 k reads of ~10 kbp per GPU = the stated 1 M reads on 8 GPUs
 WORKLOADS["c3"] = dict(WORKLOADS["c3small"], G=12_000_000, reads=125_000)
+WORKLOADS["c3big"] = dict(WORKLOADS["c3small"], G=16_000_000, reads=125_000)   # n = 2.05e9: just under the sorter's 2^31 limit
 for _s in (1, 100):   # configs[3]: sub-sample sweep on the 32-haplotype index (tunnel marking; `all` mode is covered by golden fixtures)
     WORKLOADS[f"c4_s{_s}"] = dict(WORKLOADS["c2"], split_rate=_s)
 for _s in (1, 10, 100):   # non-tunnel marking: marks come from the product's own GPU col_split (-m all), table from from_primaries
@@ -71,6 +72,7 @@ WORKLOAD_TEXT = {
     "c2": "configs[1]: 32-haplotype x 10 Mbp pangenome (+revcomp, 0.1% SNP/indel divergence), tunnels -s 10, 10M x 150 bp reads, 1% substitutions",
     "c2small": "configs[1] scaled down 10x in genome length and 5x in reads (smoke runs only)",
     "c3": "configs[2]: 64-haplotype x 12 Mbp tree-structured pangenome (+revcomp, n = 1.54e9: the largest the tooling's GPU suffix sorter fits in 180 GB; stated 50 Mbp), per GPU 125k x ~10 kbp (log-normal) nanopore-like reads at 5% error = the stated 1M reads on 8 GPUs",
+    "c3big": "configs[2]: 64-haplotype x 16 Mbp tree-structured pangenome (+revcomp, n = 2.05e9), per GPU 125k x ~10 kbp nanopore-like reads at 5% error",
     "c3small": "configs[2] scaled down: 64-haplotype x 5 Mbp tree-structured pangenome, 400k x 10 kbp (log-normal lengths) nanopore-like reads at 5% error",
 }
 
@@ -335,11 +337,11 @@ def cli_baselines(path: str, seqs, off, cpu_seconds: float):
     import oracle
     out = {}
     prefix = path[: -len(".col_pml")] if path.endswith(".col_pml") else path
-    for key, exe, budget_reads in (("nomt_e2e", "pml_query_nomt", 200_000), ("as_shipped", "pml_query", 1_500)):
+    for key, exe, budget_bases in (("nomt_e2e", "pml_query_nomt", 30_000_000), ("as_shipped", "pml_query", 225_000)):
         binp = oracle.ref_bin(exe)
         if not os.path.exists(binp):
             continue
-        k = int(min(off.size - 1, budget_reads))
+        k = int(max(1, min(off.size - 1, np.searchsorted(off, np.uint64(budget_bases), side="right") - 1)))
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "sample.fa")
             with open(fa, "wb") as f:
@@ -552,11 +554,15 @@ def main():
     lens_all = np.diff(off).astype(np.int64)
     h2d = int(16 * n_reads + (n_bases if device_pack else ((lens_all + 15) // 16).sum() * 4))
     # same call with fewer ranks active: what one rank gets with the host to itself, and the curve in between
-    e2e_curve = {}
+    e2e_curve, kernel_curve = {}, {}
     if world > 1:
         ks = sorted({1} | ({kk for kk in (2, 4) if kk < world} if a.sweep_out else set()))
         for kk in ks:
             e2e_curve[kk] = kk * n_bases / timed(e2e_dense, kk)
+            if a.sweep_out:   # the device-resident traversal with only the first kk ranks active (ranks share nothing there)
+                barrier()
+                ms_k = max_over_ranks(run_batches(a.steps) if rank < kk else 0.0)
+                kernel_curve[kk] = kk * n_bases / (ms_k * 1e-3)
 
     # ---- the compact result (one match bit per base + sparse chain ids): the same call for consumers that need no dense arrays
     c_cap = int(cb._L.colbwt_compact_bound(off.ctypes.data, n_reads))
@@ -581,8 +587,10 @@ def main():
                 "packing": c_pack, "parity_after_host_expand": c_parity,
                 "api": "colbwt_query_compact (pinned host buffers): match bit per base + non-zero chain ids; colbwt_compact_expand rebuilds the dense arrays"}
         if world > 1:
-            comp["alone_value"] = n_bases / timed(e2e_compact, 1)
+            c_curve = {kk: kk * n_bases / timed(e2e_compact, kk) for kk in sorted(e2e_curve)}
+            comp["alone_value"] = c_curve[1]
             comp["efficiency_vs_alone"] = round(comp["value"] / (world * comp["alone_value"]), 4)
+            comp["active_ranks_curve"] = {str(kk): v for kk, v in c_curve.items()}
     except cb.ColBwtError as e:
         comp = {"error": str(e)}
     d2h = n_bases * (width + 1) if transport == "dense" else int(used) if comp and "error" not in comp else None
@@ -662,9 +670,16 @@ def main():
         "wall_s_kernel_region": wall_kernel,
     }
     if a.sweep_out and world > 1:
+        # the same job with only the first k ranks active (the others idle at the barriers): one line per k, same keys as the
+        # full line where they apply; per-rank host threads stay those of the N-rank launch (stated in config.host)
         with open(a.sweep_out, "a") as f:
             for kk, v in sorted(e2e_curve.items()):
-                f.write(json.dumps({"workload": a.workload, "active_ranks": kk, "of": world, "e2e_value": v, "unit": "bases/s"}) + "\n")
+                line = {"metric": out["metric"], "value": kernel_curve.get(kk), "unit": "bases/s", "n_gpus": kk, "launched_ranks": world, "steps": a.steps,
+                        "scaling": "weak", "config": out["config"], "e2e": {"value": v, "unit": "bases/s"},
+                        "e2e_compact": {"value": comp["active_ranks_curve"][str(kk)], "unit": "bases/s"} if comp and "active_ranks_curve" in comp else None,
+                        "parity_vs_oracle": out["parity_vs_oracle"]}
+                f.write(json.dumps(line) + "\n")
+            f.write(json.dumps(out) + "\n")
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 
@@ -477,6 +478,10 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
         return COLBWT_ERR_ARG;
     }
     const std::string p(prefix);
+    const bool trace = getenv("COLBWT_TRACE") && atoi(getenv("COLBWT_TRACE")) > 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_read = 0, t_table = 0, t_walk = 0, t_resolve = 0;
     std::vector<uint8_t> heads, raw;
     std::vector<uint64_t> lens, mums;
     if (!read_all(p + ".bwt.heads", heads) || heads.empty()) {
@@ -525,6 +530,7 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
         return COLBWT_ERR_CUDA;
     }
     CB_CUDA(cudaSetDevice(device));
+    t_read = now() - t_begin;
 
     // ---- FL table on the device ------------------------------------------------------------------------------
     DevFree mem;
@@ -571,6 +577,9 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
     k_fl_columns<<<gr, 256>>>(d_order, d_lstart, t);
     CB_CUDA(cudaGetLastError());
 
+    if (trace) CB_CUDA(cudaDeviceSynchronize());
+    t_table = now() - t_begin - t_read;
+
     // ---- frontier walk ---------------------------------------------------------------------------------------------
     const uint64_t cap_ranges = mode_all ? (uint64_t)n_mums * num_docs + 1024 : (uint64_t)n_mums + 1024;
     uint64_t total_cols = 0;
@@ -616,6 +625,7 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
         return COLBWT_ERR_NOMEM;
     }
     const uint64_t n_marks = h_counts[3];
+    t_walk = now() - t_begin - t_read - t_table;
 
     // ---- overlaps + run heads (on the device), then the two output files -----------------------------------------------------
     std::vector<uint64_t> words;
@@ -625,6 +635,7 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
         if (int rc = resolve_marks_device(mem, d_marks, n_marks, d_lstart, runs, n, mode_all != 0, words, ids)) return rc;
         n_bits = n;
     }
+    t_resolve = now() - t_begin - t_read - t_table - t_walk;
     FILE *f = fopen((p + ".col_runs").c_str(), "wb");
     if (!f) {
         set_error("cannot write %s.col_runs", prefix);
@@ -640,6 +651,10 @@ extern "C" int colbwt_col_split(const char *prefix, int mode_all, int split_rate
     }
     fwrite(ids.data(), 1, ids.size(), f);       // one ID_BYTES = 1 byte per set bit (col_split.hpp:147-155)
     fclose(f);
+    if (trace)
+        fprintf(stderr, "[colbwt_col_split] %u multi-MUMs (longest %llu), %llu marks: read inputs %.1f ms, FL table %.1f ms, walk %.1f ms, resolve %.1f ms, write %.1f ms\n",
+                n_mums, (unsigned long long)max_len, (unsigned long long)n_marks, t_read * 1e3, t_table * 1e3, t_walk * 1e3, t_resolve * 1e3,
+                (now() - t_begin - t_read - t_table - t_walk - t_resolve) * 1e3);
     if (n_set_bits) *n_set_bits = ids.size();
     if (n_marked) {
         uint64_t m = 0;
