@@ -1,7 +1,8 @@
 """Kernel-only traversal of one bench workload (file-based or directly synthesised), for ncu captures:
     ncu ... python tools/kernel_only.py <workload> [reads]
-3 warm-up traversals, then 5 timed ones; prints one JSON line."""
-import json, os, sys
+3 warm-up traversals, then 5 timed ones; prints one JSON line (with CRC-32s of the outputs, so that library variants --
+COLBWT_LIB -- can be compared for equality)."""
+import json, os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -26,4 +27,6 @@ b = tbl.batch(seqs, off, width)
 for _ in range(3):
     b.run(1)
 ms = b.run(5)
-print(json.dumps({"workload": wl, "ms": ms, "gbases_s": seqs.size / ms / 1e6, "pml_bytes": width, "launches": b.launches}))
+pml, cid = b.download()
+crc = [zlib.crc32(memoryview(np.ascontiguousarray(pml)).cast("B")), zlib.crc32(memoryview(np.ascontiguousarray(cid)).cast("B"))]
+print(json.dumps({"workload": wl, "lib": os.environ.get("COLBWT_LIB", "default"), "crc32_pml_cid": crc, "ms": ms, "gbases_s": seqs.size / ms / 1e6, "pml_bytes": width, "launches": b.launches}))
