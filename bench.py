@@ -542,17 +542,16 @@ def main():
 
     # warm-up: the staging allocation, then one large call per mode (host / device packing x dense / compact transport):
     # the library measures each once and keeps the fastest (query.cu, tasks.h: choose_mode)
-    for _ in range(max(6, a.warmup)):
+    for _ in range(max(8, a.warmup)):   # first call allocates the staging; six (packing x transport) modes are each tried once
         e2e_dense()
     sampler.active.set()
     e2e_s = timed(e2e_dense, world)
     sampler.active.clear()
+    h2d, d2h = tbl.last_bytes               # what the library asked the copy engines to move in the last call
     e2e_value = world * n_bases / e2e_s
     e2e_parity = bool(np.array_equal(h_pml.array[pos_sel].astype(np.uint32), want[0]) and np.array_equal(h_cid.array[pos_sel], want[1]))
     device_pack = tbl.last_packing == "device"
     transport = tbl.last_transport
-    lens_all = np.diff(off).astype(np.int64)
-    h2d = int(16 * n_reads + (n_bases if device_pack else ((lens_all + 15) // 16).sum() * 4))
     # same call with fewer ranks active: what one rank gets with the host to itself, and the curve in between
     e2e_curve, kernel_curve = {}, {}
     if world > 1:
@@ -579,11 +578,12 @@ def main():
             e2e_compact()
         c_s = timed(e2e_compact, world)
         c_pack = tbl.last_packing
+        c_h2d, c_d2h = tbl.last_bytes
         cp, cc = cb.compact_expand(h_comp.array[:used], off, width)
         c_parity = bool(np.array_equal(cp[pos_sel].astype(np.uint32), want[0]) and np.array_equal(cc[pos_sel], want[1]))
         del cp, cc
-        comp = {"value": world * n_bases / c_s, "unit": "bases/s", "s_per_step": c_s, "d2h_bytes_per_step": int(used),
-                "h2d_bytes_per_step": int(16 * n_reads + (n_bases if c_pack == "device" else ((lens_all + 15) // 16).sum() * 4)),
+        comp = {"value": world * n_bases / c_s, "unit": "bases/s", "s_per_step": c_s, "d2h_bytes_per_step": int(c_d2h), "result_bytes": int(used),
+                "h2d_bytes_per_step": int(c_h2d),
                 "packing": c_pack, "parity_after_host_expand": c_parity,
                 "api": "colbwt_query_compact (pinned host buffers): match bit per base + non-zero chain ids; colbwt_compact_expand rebuilds the dense arrays"}
         if world > 1:
@@ -593,7 +593,6 @@ def main():
             comp["active_ranks_curve"] = {str(kk): v for kk, v in c_curve.items()}
     except cb.ColBwtError as e:
         comp = {"error": str(e)}
-    d2h = n_bases * (width + 1) if transport == "dense" else int(used) if comp and "error" not in comp else None
     sampler.stop_flag.set()
 
     if rank != 0:
@@ -642,6 +641,7 @@ def main():
                 cpu["cli_error"] = repr(e)
 
     e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s,
+           "bytes_are": "per GPU, counted by the library from the copies it enqueues (colbwt_index_last_bytes)",
            "pml_bytes": width, "packing": "device" if device_pack else "host", "transport": transport,
            "api": "colbwt_query (host pinned buffers in, dense PML + chain-id arrays out; read packing inside the timed region)"}
     if world > 1:

@@ -55,6 +55,7 @@ EXPORTS = {
     "colbwt_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
     "colbwt_index_last_packing": (C.c_int, [C.c_void_p]),
     "colbwt_index_last_transport": (C.c_int, [C.c_void_p]),
+    "colbwt_index_last_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "colbwt_compact_bound": (C.c_size_t, [C.c_void_p, C.c_uint64]),
     "colbwt_query_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "colbwt_compact_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
@@ -65,6 +66,7 @@ EXPORTS = {
     "colbwt_batch_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "colbwt_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "colbwt_batch_launches": (C.c_int, [C.c_void_p]),
+    "colbwt_batch_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "colbwt_batch_free": (None, [C.c_void_p]),
     "colbwt_format_stats": (C.c_size_t, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_uint64]),
     "colbwt_gather_bench": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
@@ -146,6 +148,14 @@ class Batch:
     @property
     def launches(self) -> int:
         return _L.colbwt_batch_launches(self._h)
+
+    @property
+    def counters(self) -> dict:
+        """Long-read bookkeeping: work items scheduled longest-first, reads cut into chunk tasks, chunk tasks re-traversed by
+        the last run (speculative start did not converge), chunk tasks."""
+        out = (C.c_uint64 * 4)()
+        _check(_L.colbwt_batch_counters(self._h, out), "colbwt_batch_counters")
+        return {"scheduled": int(out[0]), "split_reads": int(out[1]), "retraversed": int(out[2]), "chunk_tasks": int(out[3])}
 
     def download(self):
         pml = np.zeros(self.n_bases, _PML_DTYPE[self.pml_width])
@@ -255,8 +265,16 @@ class ColPml:
 
     @property
     def last_transport(self) -> str:
-        """How the dense results of the last query() crossed the link: "dense" or "compact" (expanded on the host)."""
-        return "compact" if _L.colbwt_index_last_transport(self._h) == 1 else "dense"
+        """How the dense results of the last query() crossed the link: "dense", "compact" (expanded on the host) or
+        "pml-dense+cid-compact" (PML copied as it is, only the sparse chain ids in compact form)."""
+        return {0: "dense", 1: "compact", 2: "pml-dense+cid-compact"}.get(_L.colbwt_index_last_transport(self._h), "?")
+
+    @property
+    def last_bytes(self) -> tuple:
+        """(host-to-device, device-to-host) bytes the last query() / query_compact() asked the copy engines to move."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(_L.colbwt_index_last_bytes(self._h, C.byref(a), C.byref(b)), "colbwt_index_last_bytes")
+        return int(a.value), int(b.value)
 
     @property
     def last_packing(self) -> str:

@@ -5,6 +5,7 @@
 // the read right to left, and stores the length AFTER that update.  So with nm(j) = the first mismatching base at or
 // right of j (or the read length if there is none), PML[j] = nm(j) - j: a descending ramp ending in 0 at every
 // mismatch, and ending in 1 at the last base of a read whose tail matches.  Chain ids are copied (non-zero) or 0.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 
@@ -149,6 +150,27 @@ static void expand_reads_t(const uint32_t *match, const uint32_t *cid_words, con
                 cid[pos + b] = values[k++];
             }
             pos = word_end;
+        }
+    }
+}
+
+// Chain ids only (the transport that copies PML as it is): every group of 2048 bases is zeroed and its non-zero ids are
+// dropped in from values[prefix[g] ...]; no read boundary matters.
+void expand_cid_groups(const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, uint64_t n_bases, uint64_t g0, uint64_t g1, uint8_t *cid)
+{
+    const uint64_t n_words = (n_bases + 31) / 32;
+    for (uint64_t g = g0; g < g1; ++g) {
+        const uint64_t w0 = g * COMPACT_GROUP_WORDS, w1 = std::min<uint64_t>(n_words, w0 + COMPACT_GROUP_WORDS);
+        const uint64_t b0 = w0 * 32, b1 = std::min<uint64_t>(n_bases, w1 * 32);
+        memset(cid + b0, 0, b1 - b0);
+        uint64_t k = prefix[g];
+        for (uint64_t w = w0; w < w1; ++w) {
+            uint32_t bits = cid_words[w];
+            while (bits) {
+                const uint32_t b = (uint32_t)__builtin_ctz(bits);
+                bits &= bits - 1;
+                cid[w * 32 + b] = values[k++];
+            }
         }
     }
 }

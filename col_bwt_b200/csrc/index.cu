@@ -244,7 +244,11 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
     // ---- stream the raw rows through two pinned staging buffers --------------------------------------------
     const uint64_t chunk_rows = std::min<uint64_t>(CHUNK_ROWS, r);
     uint8_t *h_stage[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
+    struct StageEvents {   // destroyed on every exit path (CB_CUDA returns early)
+        cudaEvent_t e[2] = {nullptr, nullptr};
+        ~StageEvents() { for (auto x : e) if (x) cudaEventDestroy(x); }
+        cudaEvent_t &operator[](int i) { return e[i]; }
+    } done;
     for (int s = 0; s < 2; ++s) {
         CB_CUDA(cudaMallocHost(&h_stage[s], chunk_rows * REF_ROW_BYTES));
         sc.pinned.push_back(h_stage[s]);
@@ -295,7 +299,6 @@ int build_device_table(DeviceTable &dt, int device, const void *rows_host, FILE 
         CB_CUDA(cudaEventRecord(done[s], sc.streams[s]));
     }
     CB_CUDA(cudaDeviceSynchronize());
-    for (int s = 0; s < 2; ++s) cudaEventDestroy(done[s]);
     if (rc != COLBWT_OK) return rc;
 
     return finish_table(dt, d_dest, d_doff, d_cid, n, r, stats, code_lut_out);

@@ -61,10 +61,12 @@ struct colbwt_index {
     uint8_t code_lut[256];
     std::mutex query_mutex;                 // one colbwt_query at a time per index
     colbwt::Pipeline *pipeline = nullptr;   // staging buffers + streams, kept between colbwt_query calls
-    // How colbwt_query [0] / colbwt_query_compact [1] ran (query.cu): bases/s of the last large call in each mode (bit 0:
-    // reads packed on the device, bit 1: compact transport of dense results; 0 = not measured yet), and what the last call did.
-    double mode_rate[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    // How colbwt_query [0] / colbwt_query_compact [1] ran (query.cu): bases/s of the last large call in each mode
+    // (0 = not measured yet), and what the last call did.
+    // mode = packing bit + 2 x transport (0 dense copies, 1 compact form expanded on the host, 2 PML dense + chain ids compact)
+    double mode_rate[2][8] = {{0.0}, {0.0}};
     int last_packing = 0, last_transport = 0;
+    uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // bytes the last call asked the copy engines to move
 };
 
 namespace colbwt {
@@ -105,6 +107,8 @@ int launch_compact(const void *d_pml, int pml_width, const uint8_t *d_cid, uint6
 // expand.cpp: reads [ra, rb) of the segment starting at read r_first, back to dense arrays (pml / cid point at the segment's base 0).
 void expand_reads(const uint32_t *match, const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, const uint64_t *off,
                   uint64_t r_first, uint64_t ra, uint64_t rb, void *pml, int pml_width, uint8_t *cid);
+// Chain ids alone, prefix groups [g0, g1) of a chunk of n_bases bases (cid points at the chunk's base 0).
+void expand_cid_groups(const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, uint64_t n_bases, uint64_t g0, uint64_t g1, uint8_t *cid);
 
 // Kernels launched through host wrappers (traverse.cu).
 // Device-side packing of a chunk's raw bytes (traverse.cu: k_pack_reads).

@@ -187,18 +187,13 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
     }
     // Long reads: cut into chunk tasks when one read's serial chain would dominate the batch (tasks.h).
     st.plan.clear();
-    const SplitParams sp = SplitParams::from_env();   // read per call: tests switch it with the environment
-    if (sp.wanted(st.max_len, n_bases, lanes)) {
+    const SplitParams sp0 = SplitParams::from_env();   // read per call: tests switch it with the environment
+    if (sp0.wanted(st.max_len, n_bases, lanes)) {
+        const SplitParams sp = sp0.adapted(n_bases, lanes);   // chunk length follows a lane's share of the batch (tasks.h)
         for (uint64_t i = 0; i < n_reads; ++i)
-            if (st.meta[i].len >= sp.min_len) {
-                st.plan.add_read(st.meta[i].out_off, st.meta[i].in_off, st.meta[i].len, true, sp);
-                st.meta[i].len = 0;
-            }
+            if (st.plan.add(st.meta[i].out_off, st.meta[i].in_off, st.meta[i].len, true, sp)) st.meta[i].len = 0;
         for (uint64_t i = 0; i < st.n_irregular; ++i)
-            if (st.meta_b[i].len >= sp.min_len) {
-                st.plan.add_read(st.meta_b[i].out_off, st.meta_b[i].in_off, st.meta_b[i].len, false, sp);
-                st.meta_b[i].len = 0;
-            }
+            if (st.plan.add(st.meta_b[i].out_off, st.meta_b[i].in_off, st.meta_b[i].len, false, sp)) st.meta_b[i].len = 0;
         st.plan.finish();
     }
     // Lanes take reads in meta order (global cursor): with reads of very different lengths, start the longest first so
@@ -268,13 +263,14 @@ static int upload_plan(const TaskPlan &plan, DevicePlan &dp, BatchView &bv, cuda
     bv.n_tasks = plan.n_tasks;
     bv.n_tasks_b = plan.n_tasks_b;
     bv.n_chains = (uint32_t)plan.chains.size();
-    if (plan.by_slot.empty()) {
+    if (plan.tasks.empty()) {
         bv.tasks = bv.by_slot = nullptr;
         bv.start_state = bv.end_state = nullptr;
         bv.chains = nullptr;
         return COLBWT_OK;
     }
-    const size_t nt = plan.by_slot.size(), nc = plan.chains.size();
+    // the scheduling list also holds the whole reads that take part in the longest-first order (no slot, no chain)
+    const size_t nt = plan.tasks.size(), ns = plan.by_slot.size(), nc = plan.chains.size();
     if (nt > dp.cap_tasks || nc > dp.cap_chains) {
         CB_CUDA(cudaStreamSynchronize(stream));
         dp.release();
@@ -287,8 +283,8 @@ static int upload_plan(const TaskPlan &plan, DevicePlan &dp, BatchView &bv, cuda
         CB_CUDA(cudaMalloc(&dp.chains, dp.cap_chains * sizeof(ChainDesc)));
     }
     CB_CUDA(cudaMemcpyAsync(dp.tasks, plan.tasks.data(), nt * sizeof(ChunkTask), cudaMemcpyHostToDevice, stream));
-    CB_CUDA(cudaMemcpyAsync(dp.by_slot, plan.by_slot.data(), nt * sizeof(ChunkTask), cudaMemcpyHostToDevice, stream));
-    CB_CUDA(cudaMemcpyAsync(dp.chains, plan.chains.data(), nc * sizeof(ChainDesc), cudaMemcpyHostToDevice, stream));
+    if (ns) CB_CUDA(cudaMemcpyAsync(dp.by_slot, plan.by_slot.data(), ns * sizeof(ChunkTask), cudaMemcpyHostToDevice, stream));
+    if (nc) CB_CUDA(cudaMemcpyAsync(dp.chains, plan.chains.data(), nc * sizeof(ChainDesc), cudaMemcpyHostToDevice, stream));
     bv.tasks = dp.tasks;
     bv.by_slot = dp.by_slot;
     bv.start_state = dp.start_state;
@@ -311,7 +307,7 @@ struct colbwt_batch {
     BatchView view{};
     void *d_meta = nullptr, *d_meta_b = nullptr, *d_words = nullptr, *d_bytes = nullptr, *d_pml = nullptr, *d_cid = nullptr;
     unsigned long long *d_cursors = nullptr;
-    uint64_t n_bases = 0;
+    uint64_t n_bases = 0, n_slot_tasks = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     DevicePlan plan;
@@ -426,6 +422,8 @@ extern "C" int colbwt_batch_upload(colbwt_index *idx, int device_slot, const uin
     b->view.n_packed = (uint32_t)n_reads;
     b->view.n_bytes = (uint32_t)st.n_irregular;
     if (int rc = upload_plan(st.plan, b->plan, b->view, b->stream)) return rc;
+    b->n_slot_tasks = st.plan.by_slot.size();
+    CB_CUDA(cudaMemset(b->d_cursors, 0, 4 * sizeof(unsigned long long)));
     CB_CUDA(cudaStreamSynchronize(b->stream));
     *out = b.release();
     return COLBWT_OK;
@@ -435,6 +433,22 @@ extern "C" int colbwt_batch_launches(const colbwt_batch *b)
 {
     if (!b) return 0;
     return ((b->view.n_packed || b->view.n_tasks) ? 1 : 0) + ((b->view.n_bytes || b->view.n_tasks_b) ? 1 : 0) + (b->view.n_chains ? 1 : 0);
+}
+
+extern "C" int colbwt_batch_counters(colbwt_batch *b, uint64_t out[4])
+{
+    if (!b || !out) {
+        set_error("colbwt_batch_counters: null argument");
+        return COLBWT_ERR_ARG;
+    }
+    CB_CUDA(cudaSetDevice(b->idx->dev[b->slot].device));
+    unsigned long long redone = 0;
+    CB_CUDA(cudaMemcpy(&redone, b->d_cursors + 2, sizeof(redone), cudaMemcpyDeviceToHost));
+    out[0] = (uint64_t)b->view.n_tasks + b->view.n_tasks_b;
+    out[1] = b->view.n_chains;
+    out[2] = redone;
+    out[3] = b->n_slot_tasks;
+    return COLBWT_OK;
 }
 
 extern "C" int colbwt_batch_run(colbwt_batch *b, int iters, float *ms_per_iter)
@@ -493,7 +507,8 @@ static const int SLOTS_PER_DEVICE = getenv("COLBWT_SLOTS") ? std::max(1, std::mi
 enum OutKind {
     OUT_DENSE = 0,              // dense PML + CID arrays, copied as they are (2-5 bytes per base over PCIe)
     OUT_DENSE_VIA_COMPACT = 1,  // dense arrays for the caller, but the link carries the compact form and the host threads expand it
-    OUT_COMPACT = 2             // colbwt_query_compact: the compact form is the result
+    OUT_COMPACT = 2,            // colbwt_query_compact: the compact form is the result
+    OUT_DENSE_CID_COMPACT = 3   // dense arrays for the caller: PML copied as it is, chain ids (sparse) cross the link in compact form
 };
 
 struct Slot {
@@ -635,7 +650,7 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
 
 // ---- chunk planning -------------------------------------------------------------------------------------------
 struct Chunk { uint64_t r0, r1; };
-struct Geometry { uint64_t chunk_bases = 0, chunk_reads = 0; uint32_t max_len = 0; };
+struct Geometry { uint64_t chunk_bases = 0, chunk_reads = 0, grow_bases = 0, min_reads = 0; uint32_t max_len = 0; };
 
 // One pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB.
 static int scan_offsets(const uint64_t *off, uint64_t n_reads, uint32_t *max_len_out)
@@ -675,28 +690,46 @@ static Geometry chunk_geometry(uint64_t total_bases, uint64_t n_reads, uint32_t 
     uint64_t chunk_bases = 96ull << 20;   // measured on C2 (profiles/r1/e2e_chunk_sweep.log): 16/24/32/48/96/128/192 M -> 83.6/85.0/81.1/76.3/71.8-73.2/72.0/73.1 ms
     const char *env = getenv("COLBWT_CHUNK_BASES");
     if (env) chunk_bases = std::max<uint64_t>(1024, strtoull(env, nullptr, 10));
-    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read at a time and
-    // six chunks are in flight), so the chunk grows with the mean read length: 32 Ki reads per chunk, up to 512 Mbases.
-    if (!env) chunk_bases = std::max<uint64_t>(chunk_bases, std::min<uint64_t>(512ull << 20, (total_bases / std::max<uint64_t>(1, n_reads)) * 32768));
-    if (staged_bytes_per_base && !env) chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / staged_bytes_per_base);
+    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read or chunk task at a
+    // time and several chunks are in flight), so a chunk that reaches chunk_bases with fewer than 32 Ki reads keeps growing,
+    // up to 512 Mbases.  Decided chunk by chunk (plan_chunks), not from the batch's mean read length: in a mixed batch
+    // (configs[4]: 12.4 M short reads followed by 125 k long ones) the long reads would otherwise be cut into 96-Mbase
+    // chunks of 9.6 k reads each, every one of them as slow as its longest serial chain.
+    uint64_t grow_bases = env ? chunk_bases : (512ull << 20);
+    if (staged_bytes_per_base && !env) {
+        chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / staged_bytes_per_base);
+        grow_bases = std::min<uint64_t>(grow_bases, (256ull << 20) / staged_bytes_per_base);
+    }
     chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
     chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
     g.chunk_bases = chunk_bases;
+    g.grow_bases = std::min<uint64_t>(std::max(grow_bases, chunk_bases), std::max<uint64_t>(total_bases, 16));
+    g.min_reads = 32768;
     // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
     g.chunk_reads = std::min<uint64_t>(std::max<uint64_t>(chunk_bases / 32, 1024), n_reads);
     return g;
 }
 
-static void plan_chunks(const uint64_t *off, uint64_t n_reads, const Geometry &g, std::vector<Chunk> &chunks)
+// Cuts the batch into chunks and leaves the capacities the staging needs (largest chunk in bases and in reads) in g.
+static void plan_chunks(const uint64_t *off, uint64_t n_reads, Geometry &g, std::vector<Chunk> &chunks)
 {
     chunks.clear();
-    for (uint64_t r0 = 0; r0 < n_reads;) {   // at most chunk_bases bases and chunk_reads reads, at least one read
+    uint64_t cap_bases = 16, cap_reads = 1;
+    for (uint64_t r0 = 0; r0 < n_reads;) {   // at most chunk_bases bases (grow_bases while short of min_reads reads) and chunk_reads reads, at least one read
         uint64_t r1 = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + g.chunk_bases) - off) - 1;
+        if (r1 - r0 < g.min_reads && g.grow_bases > g.chunk_bases) {
+            const uint64_t far = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + g.grow_bases) - off) - 1;
+            r1 = std::max(r1, std::min(far, r0 + g.min_reads));
+        }
         r1 = std::min(r1, r0 + g.chunk_reads);
         if (r1 <= r0) r1 = r0 + 1;
         chunks.push_back(Chunk{r0, r1});
+        cap_bases = std::max(cap_bases, off[r1] - off[r0]);
+        cap_reads = std::max(cap_reads, r1 - r0);
         r0 = r1;
     }
+    g.chunk_bases = cap_bases;
+    g.chunk_reads = cap_reads;
 }
 
 // ---- one call ---------------------------------------------------------------------------------------------------
@@ -716,6 +749,7 @@ struct QueryJob {
     colbwt_compact_segment *segments = nullptr;            // directory inside cbuf
     std::atomic<uint64_t> values_cursor{0};                // bump allocator for the value regions inside cbuf
     std::vector<Chunk> chunks;
+    std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};      // what the copy engines were asked to move (colbwt_index_last_bytes)
     std::atomic<size_t> next_chunk{0};
     std::atomic<int> rc{COLBWT_OK};
     std::mutex err_m;
@@ -770,6 +804,7 @@ static int finish_values(QueryJob &J, Slot &k)
         if (direct) dst = J.cbuf + k.values_off;
     }
     if (k.n_values) CB_CUDA(cudaMemcpyAsync(dst, k.d_values, k.n_values, cudaMemcpyDeviceToHost, k.stream));
+    J.d2h_bytes += k.n_values;
     if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
     CB_CUDA(cudaEventRecord(k.done, k.stream));
     k.phase = 2;
@@ -809,7 +844,15 @@ static int drain(QueryJob &J, Slot &k, QueryJob::DevTimes &tm)
         }
     } else if (k.out_bases) {
         const CompactLayout lay(k.out_bases);
-        if (J.kind == OUT_DENSE_VIA_COMPACT) {
+        if (J.kind == OUT_DENSE_CID_COMPACT) {
+            // PML has landed in the caller's array by DMA; the chain ids are rebuilt group by group (2048 bases each)
+            const uint8_t *fx = k.h_out, *vals = k.h_out + J.pl->compact_fixed_cap;
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, lay.n_groups / 16));
+            pool.parallel_for(T, [&](int t) {
+                expand_cid_groups(reinterpret_cast<const uint32_t *>(fx + lay.cid_off), reinterpret_cast<const uint32_t *>(fx + lay.prefix_off), vals, k.out_bases,
+                                  lay.n_groups * (uint64_t)t / (uint64_t)T, lay.n_groups * (uint64_t)(t + 1) / (uint64_t)T, J.cid + k.out_base);
+            });
+        } else if (J.kind == OUT_DENSE_VIA_COMPACT) {
             const uint8_t *fx = k.h_out, *vals = k.h_out + J.pl->compact_fixed_cap;
             const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, k.out_bases >> 16));
             const std::vector<uint64_t> cut = slice_reads(J.off, c.r0, c.r1, T);
@@ -854,6 +897,8 @@ static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTi
 
     if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[0], k.stream));
     CB_CUDA(cudaMemcpyAsync(k.d_meta, k.h_meta, st.n_reads * sizeof(ReadMeta), cudaMemcpyHostToDevice, k.stream));
+    J.h2d_bytes += st.n_reads * sizeof(ReadMeta) + (J.device_pack ? st.n_bases : st.n_words * 4 + st.n_irregular * sizeof(ReadMeta) + st.n_byte_bases) +
+                   st.plan.tasks.size() * sizeof(ChunkTask) + st.plan.by_slot.size() * sizeof(ChunkTask) + st.plan.chains.size() * sizeof(ChainDesc);
     if (J.device_pack) {
         CB_CUDA(cudaMemcpyAsync(k.d_bytes, J.seqs + off[c.r0], st.n_bases, cudaMemcpyHostToDevice, k.stream));
         if (int rc = launch_pack(dt, k.d_bytes, k.d_meta, (uint32_t)st.n_reads, k.d_words, k.d_meta_b, (uint32_t *)(k.d_cursors + 3), k.stream)) return rc;
@@ -893,8 +938,20 @@ static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTi
             CB_CUDA(cudaMemcpyAsync(J.pml + ob * (uint64_t)J.pml_width, k.d_pml, st.n_bases * (uint64_t)J.pml_width, cudaMemcpyDeviceToHost, k.stream));
             CB_CUDA(cudaMemcpyAsync(J.cid + ob, k.d_cid, st.n_bases, cudaMemcpyDeviceToHost, k.stream));
         }
+        J.d2h_bytes += st.n_bases * (uint64_t)(J.pml_width + 1);
         if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
         CB_CUDA(cudaEventRecord(k.done, k.stream));
+    } else if (st.n_bases && J.kind == OUT_DENSE_CID_COMPACT) {
+        // PML goes out dense (the copy engine writes it where the caller wants it); of the chain ids only the non-zero ones
+        // cross the link (bit words + per-group prefix now, the values once their number is known: finish_values)
+        const CompactLayout lay(st.n_bases);
+        if (int rc = launch_compact(k.d_pml, J.pml_width, k.d_cid, st.n_bases, k.d_compact, k.d_group_count, k.d_scan_temp, pl.scan_temp_bytes, k.d_values, k.stream)) return rc;
+        if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
+        CB_CUDA(cudaMemcpyAsync(k.h_out + lay.cid_off, k.d_compact + lay.cid_off, lay.fixed_bytes - lay.cid_off, cudaMemcpyDeviceToHost, k.stream));
+        CB_CUDA(cudaEventRecord(k.fixed_done, k.stream));
+        CB_CUDA(cudaMemcpyAsync(J.pml + ob * (uint64_t)J.pml_width, k.d_pml, st.n_bases * (uint64_t)J.pml_width, cudaMemcpyDeviceToHost, k.stream));
+        J.d2h_bytes += lay.fixed_bytes - lay.cid_off + st.n_bases * (uint64_t)J.pml_width;
+        k.phase = 1;
     } else if (st.n_bases) {
         // dense results stay in HBM; the link carries the compact form (compact.cu) in two steps: the fixed-size part
         // now, the non-zero chain ids once their number is known (finish_values)
@@ -903,6 +960,7 @@ static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTi
         if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
         uint8_t *dst = (J.kind == OUT_COMPACT && J.cbuf_pinned) ? J.cbuf + J.segments[ci].match_off : k.h_out;
         CB_CUDA(cudaMemcpyAsync(dst, k.d_compact, lay.fixed_bytes, cudaMemcpyDeviceToHost, k.stream));
+        J.d2h_bytes += lay.fixed_bytes;
         CB_CUDA(cudaEventRecord(k.fixed_done, k.stream));
         k.phase = 1;
     } else {
@@ -978,7 +1036,9 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     if (int rc = check_width(pml_width, max_len)) return rc;
     // pageable result buffers are reached through one pinned staging area per slot
     const bool pageable_out = !compact_api && !(is_pinned(cs.pml) && is_pinned(cs.cid));
-    const Geometry geo = chunk_geometry(total_bases, n_reads, max_len, pageable_out ? (uint64_t)(pml_width + 1) : 0);
+    Geometry geo = chunk_geometry(total_bases, n_reads, max_len, pageable_out ? (uint64_t)(pml_width + 1) : 0);
+    std::vector<Chunk> planned;
+    plan_chunks(off, n_reads, geo, planned);   // also leaves the staging capacities (largest chunk) in geo
 
     std::lock_guard<std::mutex> guard(idx->query_mutex);
     // ---- where to pack and how to cross the link: measured, not guessed -------------------------------------------
@@ -991,35 +1051,39 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     const SplitParams sp_query = SplitParams::from_env();
     const bool can_device_pack = is_pinned(seqs) && max_len < sp_query.min_len;
     const bool large_call = total_bases >= (64ull << 20);
+    // mode = packing bit + 2 x transport; transport 0 = dense copies, 1 = compact form expanded by the host threads,
+    // 2 = PML dense + chain ids compact (needs pinned result arrays: the copy engine writes the PML in place)
+    constexpr int N_MODES = 6;
     uint32_t allowed = 0;
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < N_MODES; ++m) {
         if ((m & 1) && !can_device_pack) continue;
-        if ((m & 2) && compact_api) continue;
+        if ((m >> 1) && compact_api) continue;
+        if ((m >> 1) == 2 && pageable_out) continue;
         allowed |= 1u << m;
     }
-    auto pin_bit = [&](const char *name, int bit) {
+    auto pin_field = [&](const char *name, bool packing) {
         const char *e = getenv(name);
         if (!e) return;
         uint32_t keep = 0;
-        for (int m = 0; m < 4; ++m)
-            if (((m >> bit) & 1) == (atoi(e) != 0 ? 1 : 0)) keep |= 1u << m;
+        for (int m = 0; m < N_MODES; ++m)
+            if ((packing ? (m & 1) : (m >> 1)) == atoi(e)) keep |= 1u << m;
         if (allowed & keep) allowed &= keep;
     };
-    pin_bit("COLBWT_DEVICE_PACK", 0);
-    pin_bit("COLBWT_COMPACT_D2H", 1);
+    pin_field("COLBWT_DEVICE_PACK", true);
+    pin_field("COLBWT_COMPACT_D2H", false);
     double *rates = idx->mode_rate[compact_api ? 1 : 0];
     int rule = (Pool::get().size() < 8) ? 1 : 0;
-    const int mode = choose_mode(rule, allowed, rates, 4, large_call);   // tasks.h
+    const int mode = choose_mode(rule, allowed, rates, N_MODES, large_call);   // tasks.h
     const bool device_pack = (mode & 1) != 0;
-    const OutKind kind = compact_api ? OUT_COMPACT : ((mode & 2) ? OUT_DENSE_VIA_COMPACT : OUT_DENSE);
+    const OutKind kind = compact_api ? OUT_COMPACT : ((mode >> 1) == 1 ? OUT_DENSE_VIA_COMPACT : (mode >> 1) == 2 ? OUT_DENSE_CID_COMPACT : OUT_DENSE);
     idx->last_packing = device_pack ? 1 : 0;
-    idx->last_transport = kind == OUT_DENSE ? 0 : 1;
+    idx->last_transport = compact_api ? 1 : (mode >> 1);
 
     Pipeline *plp = nullptr;
     const bool staged_out = pageable_out && kind == OUT_DENSE;
     const Pipeline *before = idx->pipeline;
     // compact buffers are allocated as soon as a call could use them, so that trying that mode later does not reallocate
-    const bool want_compact = kind != OUT_DENSE || (allowed & 0xCu) != 0;
+    const bool want_compact = kind != OUT_DENSE || (allowed & ~0x3u) != 0;
     if (int rc = get_pipeline(idx, geo.chunk_reads, geo.chunk_bases, pml_width, staged_out, want_compact, &plp)) return rc;
     const bool fresh_pipeline = plp != before;   // this call pays for the staging allocations: not a timing sample
 
@@ -1036,7 +1100,7 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     J.pml = (uint8_t *)cs.pml;
     J.cid = cs.cid;
     J.trace = getenv("COLBWT_TRACE") ? atoi(getenv("COLBWT_TRACE")) : 0;
-    plan_chunks(off, n_reads, geo, J.chunks);
+    J.chunks = std::move(planned);
     const int n_dev = (int)idx->dev.size();
     J.times.resize((size_t)n_dev);
     if (compact_api) {
@@ -1124,10 +1188,13 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
         }
         fprintf(stderr, "[colbwt_query] %zu chunks, %.1f Mbases, total %.1f ms = %.2f Gbases/s (%s, packing on the %s, %d host threads)\n", J.chunks.size(),
                 total_bases / 1e6, t_total * 1e3, total_bases / t_total / 1e9,
-                kind == OUT_DENSE ? (staged_out ? "dense via staging" : "dense into pinned buffers") : kind == OUT_COMPACT ? "compact result" : "dense, compact transport",
+                kind == OUT_DENSE ? (staged_out ? "dense via staging" : "dense into pinned buffers") : kind == OUT_COMPACT ? "compact result"
+                : kind == OUT_DENSE_CID_COMPACT ? "dense, PML copied + chain ids compact" : "dense, compact transport",
                 device_pack ? "device" : "host", Pool::get().size());
     }
     if (large_call && !fresh_pipeline) rates[mode] = (double)total_bases / std::max(1e-9, t_total);
+    idx->last_h2d_bytes = J.h2d_bytes.load();
+    idx->last_d2h_bytes = J.d2h_bytes.load();
     return COLBWT_OK;
 }
 
@@ -1198,7 +1265,7 @@ extern "C" size_t colbwt_compact_bound(const uint64_t *off, uint64_t n_reads)
     uint32_t max_len = 0;
     if (scan_offsets(off, n_reads, &max_len) != COLBWT_OK) return 0;
     const uint64_t total = off[n_reads] - off[0];
-    const Geometry geo = chunk_geometry(total, n_reads, max_len, 0);
+    Geometry geo = chunk_geometry(total, n_reads, max_len, 0);
     std::vector<Chunk> chunks;
     plan_chunks(off, n_reads, geo, chunks);
     uint64_t at = (sizeof(colbwt_compact_header) + chunks.size() * sizeof(colbwt_compact_segment) + 15) & ~15ull;
@@ -1257,6 +1324,13 @@ extern "C" int colbwt_compact_expand(const void *result, const uint64_t *off, ui
 
 extern "C" int colbwt_index_last_packing(const colbwt_index *idx) { return idx ? idx->last_packing : -1; }
 extern "C" int colbwt_index_last_transport(const colbwt_index *idx) { return idx ? idx->last_transport : -1; }
+extern "C" int colbwt_index_last_bytes(const colbwt_index *idx, uint64_t *h2d_bytes, uint64_t *d2h_bytes)
+{
+    if (!idx) return COLBWT_ERR_ARG;
+    if (h2d_bytes) *h2d_bytes = idx->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = idx->last_d2h_bytes;
+    return COLBWT_OK;
+}
 
 extern "C" void *colbwt_host_alloc(size_t bytes)
 {

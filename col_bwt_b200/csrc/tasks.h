@@ -14,13 +14,14 @@ struct SplitParams {
     uint32_t chunk = 4096;     // ... into chunks of about this many bases ...
     uint32_t warm = 512;       // ... each started this many bases early from the initial state
     int mode = -1;             // -1 auto (split when the longest read would dominate the batch), 0 never, 1 always
+    bool pinned_chunk = false, pinned_warm = false, pinned_min = false;   // set by the environment: adapt() leaves them alone
     static SplitParams from_env()
     {
         SplitParams p;
         if (const char *e = getenv("COLBWT_SPLIT")) p.mode = atoi(e);
-        if (const char *e = getenv("COLBWT_SPLIT_CHUNK")) p.chunk = std::max(8, atoi(e));
-        if (const char *e = getenv("COLBWT_SPLIT_WARM")) p.warm = std::max(0, atoi(e));
-        if (const char *e = getenv("COLBWT_SPLIT_MIN")) p.min_len = std::max(16, atoi(e));
+        if (const char *e = getenv("COLBWT_SPLIT_CHUNK")) { p.chunk = std::max(8, atoi(e)); p.pinned_chunk = true; }
+        if (const char *e = getenv("COLBWT_SPLIT_WARM")) { p.warm = std::max(0, atoi(e)); p.pinned_warm = true; }
+        if (const char *e = getenv("COLBWT_SPLIT_MIN")) { p.min_len = std::max(16, atoi(e)); p.pinned_min = true; }
         p.min_len = std::max(p.min_len, 2 * p.chunk);
         return p;
     }
@@ -32,6 +33,28 @@ struct SplitParams {
         if (mode == 1) return true;
         return max_len * lanes > total_bases / 4;
     }
+    // Geometry for one batch.  A lane runs one task at a time, so the batch ends when the lane with the most work ends:
+    // tasks must be SHORT against a lane's share of the batch (total_bases / lanes), or the last tasks -- and every whole
+    // read nearly as long as a chunk -- run while most lanes idle.  Measured on configs[2] with 125 k reads per GPU
+    // (8.2 kbases per lane, profiles/r2/r2_longread_sweep_c3.log): chunk 4096 -> 52.7 ms, 3072 -> 41.7, 2048 -> 41.9
+    // although the shorter chunks traverse 12 % more bases; with the whole reads ordered among the tasks (add_whole) 4096 ->
+    // 39.9, 2048 -> 39.3, 1536 -> 36.4, 1024 -> 40.6 (r2_longread_sweep2.log).  So: about six tasks per lane, chunk in [1024, 4096], warm-up
+    // 256 for chunks up to 3072 (enough at the error rates that make long reads diverge; a chunk whose warm-up was too
+    // short is re-traversed by k_fixup, never wrong), and everything longer than 1.5 chunks is cut.
+    SplitParams adapted(uint64_t total_bases, uint64_t lanes) const
+    {
+        SplitParams p = *this;
+        if (!pinned_chunk) {
+            const uint64_t share = total_bases / std::max<uint64_t>(1, lanes * 6);
+            p.chunk = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1024, (share + 255) & ~255ull));
+        }
+        if (!pinned_warm) p.warm = p.chunk <= 3072 ? 256 : 512;
+        if (!pinned_min) p.min_len = std::max<uint32_t>(16, p.chunk + p.chunk / 2);
+        else p.min_len = std::max(p.min_len, 2 * p.chunk);
+        return p;
+    }
+    // Reads this long, but not long enough to be cut, still take part in the longest-first order of the chunk tasks.
+    uint32_t whole_min() const { return std::max<uint32_t>(64, chunk / 8); }
 };
 
 // How colbwt_query runs a call that could go several ways (query.cu: where the reads are packed, how the results cross
@@ -65,16 +88,21 @@ inline int choose_mode(int rule, uint32_t allowed, const double *rate, int n_mod
 
 struct TaskPlan {
     std::vector<ChunkTask> tasks;     // scheduling order: packed tasks (longest first), then byte tasks (longest first)
-    std::vector<ChunkTask> by_slot;   // slot order
+    std::vector<ChunkTask> by_slot;   // chunk tasks of the split reads in slot order
+    std::vector<ChunkTask> wholes;    // whole reads scheduled among the chunk tasks (slot = NO_SLOT: nothing to verify)
+    std::vector<char> wholes_packed;
     std::vector<ChainDesc> chains;
     uint32_t n_tasks = 0, n_tasks_b = 0;
     void clear()
     {
         tasks.clear();
         by_slot.clear();
+        wholes.clear();
+        wholes_packed.clear();
         chains.clear();
         n_tasks = n_tasks_b = 0;
     }
+    bool empty() const { return by_slot.empty() && wholes.empty(); }
     // Cut one read into chunk tasks, top chunk first.
     void add_read(uint64_t out_off, uint32_t in_off, uint32_t len, bool packed, const SplitParams &sp)
     {
@@ -90,11 +118,28 @@ struct TaskPlan {
         }
         chains.push_back(c);
     }
+    // A read that is traversed in one piece but takes its place in the longest-first order of the tasks: with the chunk
+    // tasks first and the whole reads after them, a read just short of the splitting length started when the chunk tasks
+    // were done and ran alone for the length of two chunks.
+    void add_whole(uint64_t out_off, uint32_t in_off, uint32_t len, bool packed)
+    {
+        wholes.push_back(ChunkTask{out_off, in_off, 0, len, len, NO_SLOT, len});
+        wholes_packed.push_back(packed ? 1 : 0);
+    }
+    // What the driver does with every read once a batch is being split: true = the read became one or more tasks.
+    bool add(uint64_t out_off, uint32_t in_off, uint32_t len, bool packed, const SplitParams &sp)
+    {
+        if (len >= sp.min_len) add_read(out_off, in_off, len, packed, sp);
+        else if (len >= sp.whole_min()) add_whole(out_off, in_off, len, packed);
+        else return false;
+        return true;
+    }
     void finish()
     {
         std::vector<ChunkTask> p, b;
         for (const ChainDesc &c : chains)
             for (uint32_t i = 0; i < c.n_chunks; ++i) (c.packed ? p : b).push_back(by_slot[c.first_slot + i]);
+        for (size_t i = 0; i < wholes.size(); ++i) (wholes_packed[i] ? p : b).push_back(wholes[i]);
         auto longer = [](const ChunkTask &x, const ChunkTask &y) { return x.len > y.len; };
         std::stable_sort(p.begin(), p.end(), longer);
         std::stable_sort(b.begin(), b.end(), longer);

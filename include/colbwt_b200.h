@@ -155,8 +155,12 @@ int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_re
  * calls and keeps the faster one; COLBWT_DEVICE_PACK=0|1 pins the choice.  No reference counterpart (diagnostic). */
 int colbwt_index_last_packing(const colbwt_index *idx);
 /* How the dense results of the last colbwt_query crossed the link: 0 as they are, 1 in the compact form above, expanded
- * into the caller's arrays by the library's host threads (measured the same way; COLBWT_COMPACT_D2H=0|1 pins it). */
+ * into the caller's arrays by the library's host threads, 2 PML copied as it is and only the chain ids (sparse) in compact
+ * form (needs pinned result arrays).  Measured the same way as the packing; COLBWT_COMPACT_D2H=0|1|2 pins it. */
 int colbwt_index_last_transport(const colbwt_index *idx);
+/* Bytes the last colbwt_query / colbwt_query_compact on this index asked the copy engines to move, host to device and
+ * device to host (diagnostic; what bench.py reports as h2d/d2h bytes per step). */
+int colbwt_index_last_bytes(const colbwt_index *idx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* Pinned host memory for seqs / pml / cid buffers (lets colbwt_query copy without a staging hop). */
 void *colbwt_host_alloc(size_t bytes);
@@ -174,6 +178,10 @@ int colbwt_batch_download(colbwt_batch *b, void *pml, uint8_t *cid);
 int colbwt_batch_device_ptrs(colbwt_batch *b, void **pml_dev, void **cid_dev, uint64_t *n_bases);
 /* Kernel launches issued by one traversal of this batch (for bench.py's gpu_launches). */
 int colbwt_batch_launches(const colbwt_batch *b);
+/* Long-read bookkeeping of this batch (diagnostic): out[0] = work items scheduled longest-first (chunk tasks of the reads
+ * that were cut + whole reads ordered among them), out[1] = reads that were cut, out[2] = chunk tasks whose speculative
+ * start did not converge and were re-traversed in the last colbwt_batch_run traversal, out[3] = chunk tasks of cut reads. */
+int colbwt_batch_counters(colbwt_batch *b, uint64_t out[4]);
 void colbwt_batch_free(colbwt_batch *b);
 
 /* ---- text output of pml_query (src/pml_query.cpp:79-85) -------------------------------------------------- */

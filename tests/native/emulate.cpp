@@ -48,7 +48,7 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
     const Stage sg{stage_buf, 1, 0};
     std::vector<uint32_t> words;
     std::vector<uint64_t> word_off(n_reads, 0);
-    std::vector<char> is_packed(n_reads, 0);
+    std::vector<char> is_packed(n_reads, 0), in_plan(n_reads, 0);
     uint64_t nw = 0;
     for (uint64_t i = 0; i < n_reads; ++i) { word_off[i] = nw; nw += ((off[i + 1] - off[i] + 15) >> 4); }
     words.assign(nw + 4, 0);
@@ -57,7 +57,7 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
         const uint64_t len = off[i + 1] - off[i];
         if (!len) continue;
         is_packed[i] = pack_read_2bit(seqs + off[i], len, words.data() + word_off[i]);
-        if (len >= sp.min_len) plan.add_read(off[i], is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i], (uint32_t)len, is_packed[i], sp);
+        in_plan[i] = plan.add(off[i], is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i], (uint32_t)len, is_packed[i], sp);   // split, or whole among the tasks
     }
     plan.finish();
     std::vector<ChainState> ss(plan.by_slot.size() + 1), es(plan.by_slot.size() + 1);
@@ -82,7 +82,7 @@ static uint64_t emu_split_impl(EmuTable *t, const uint8_t *seqs, const uint64_t 
     }
     for (uint64_t i = 0; i < n_reads; ++i) {   // whole reads
         const uint64_t len = off[i + 1] - off[i];
-        if (!len || len >= sp.min_len) continue;
+        if (!len || in_plan[i]) continue;
         Lane<PmlT> L;
         ReadMeta m{off[i], (uint32_t)len, is_packed[i] ? (uint32_t)word_off[i] : (uint32_t)off[i]};
         if (is_packed[i]) { lane_begin<true>(L, t->view, bv, m); lane_run<true, NARROW>(L, sg, t->view, bv, t->code_lut); }
@@ -212,6 +212,16 @@ uint32_t emu_plan(uint32_t len, uint32_t chunk, uint32_t warm, uint32_t *out, ui
         out[4 * i + 3] = plan.by_slot[i].slot;
     }
     return (uint32_t)plan.by_slot.size();
+}
+
+// Batch geometry of the long-read path (tasks.h: SplitParams::adapted): out = chunk, warm, min_len, whole_min.
+void emu_adapted(uint64_t total_bases, uint64_t lanes, uint32_t *out)
+{
+    const SplitParams sp = SplitParams().adapted(total_bases, lanes);
+    out[0] = sp.chunk;
+    out[1] = sp.warm;
+    out[2] = sp.min_len;
+    out[3] = sp.whole_min();
 }
 
 int emu_choose_mode(int rule, uint32_t allowed, const double *rate, int n_modes, int large_call)

@@ -247,6 +247,27 @@ def test_chunk_planner_tiles_the_read(length, chunk, warm):
     assert (t[:, 3] == np.arange(n)).all()
 
 
+def test_chunk_geometry_follows_the_batch():
+    """tasks.h: SplitParams::adapted -- about six tasks per lane, chunk within [1024, 4096], shorter warm-up with shorter
+    chunks, reads of 1.5 chunks or more are cut, shorter ones above chunk/8 are scheduled whole among the tasks."""
+    import ctypes as C
+    from emu import SO, build
+    build()
+    L = C.CDLL(SO)
+    L.emu_adapted.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    out = np.zeros(4, np.uint32)
+
+    def geo(bases, lanes):
+        L.emu_adapted(bases, lanes, out.ctypes.data)
+        return tuple(int(x) for x in out)
+    lanes = 148 * 1024
+    assert geo(4_000_000_000, lanes) == (4096, 512, 6144, 512)          # c3small: plenty of work per lane
+    assert geo(1_245_000_000, lanes) == (1536, 256, 2304, 192)          # configs[2] per GPU: 8.2 kbases per lane
+    assert geo(300_000_000, lanes) == (1024, 256, 1536, 128)            # small batch: floor
+    c, w, m, wm = geo(2_000_000_000, lanes)
+    assert c % 256 == 0 and 2048 <= c <= 2560 and w == 256 and m == c + c // 2
+
+
 def test_mode_choice_is_measured_then_kept():
     """tasks.h: choose_mode -- the rule first, every other allowed mode once, then the fastest (the rule keeps its place
     within 5 %).  Modes of colbwt_query: bit 0 = reads packed on the device, bit 1 = compact transport."""

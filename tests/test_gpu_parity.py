@@ -600,7 +600,36 @@ def test_dense_query_over_compact_transport(cb, small_index, monkeypatch, device
     assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
 
 
-@pytest.mark.parametrize("compact", ["0", "1"])
+@pytest.mark.parametrize("device_pack", ["0", "1"])
+def test_dense_query_with_compact_chain_ids(cb, small_index, monkeypatch, device_pack):
+    """COLBWT_COMPACT_D2H=2: PML is copied into the caller's pinned array as it is, the chain ids cross the link as bit
+    words + non-zero values and are rebuilt group by group on the host.  Pageable result arrays cannot take this route
+    (the copy engine writes the PML in place) and fall back to another transport; results are the same either way."""
+    monkeypatch.setenv("COLBWT_COMPACT_D2H", "2")
+    monkeypatch.setenv("COLBWT_DEVICE_PACK", device_pack)
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "70000")
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    for seqs, off in _compact_cases(small_index):
+        want_p, want_c = orc.query_batch(seqs, off)
+        h_seqs = cb.PinnedArray(seqs.size, np.uint8)
+        h_seqs.array[:] = seqs
+        widths = (cb.PML_U8, cb.PML_U16, cb.PML_U32) if int(np.diff(off).max()) < 256 else (cb.PML_U16, cb.PML_U32)
+        for width in widths:
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width]
+            pp, pc = cb.PinnedArray(seqs.size, dt), cb.PinnedArray(seqs.size, np.uint8)
+            pc.array[:] = 0xEE                                            # every byte must be rewritten, zeros included
+            tbl.query(h_seqs.array, off, width, out=(pp.array, pc.array))
+            assert tbl.last_transport == "pml-dense+cid-compact"
+            assert np.array_equal(pp.array.astype(np.uint32), want_p) and np.array_equal(pc.array, want_c)
+            h2d, d2h = tbl.last_bytes
+            assert h2d > 0 and seqs.size * width < d2h < seqs.size * (width + 1) + 4096 * (1 + seqs.size // 70000)
+        pml, cid = tbl.query(seqs, off, cb.PML_U16)                      # pageable results: another transport serves them
+        assert tbl.last_transport != "pml-dense+cid-compact"
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("compact", ["0", "1", "2"])
 def test_two_replicas_on_one_gpu_feeder_threads(cb, small_index, monkeypatch, compact):
     """Two replicas of the table on the SAME device: exercises the per-device feeder threads of colbwt_query (one per
     replica, chunks taken from a shared counter) on a single-GPU box; results must land in input order."""
@@ -613,6 +642,11 @@ def test_two_replicas_on_one_gpu_feeder_threads(cb, small_index, monkeypatch, co
     for _ in range(3):
         pml, cid = tbl.query(seqs, off)
         assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    h_seqs = cb.PinnedArray(seqs.size, np.uint8)
+    h_seqs.array[:] = seqs
+    pp, pc = cb.PinnedArray(seqs.size, np.uint16), cb.PinnedArray(seqs.size, np.uint8)
+    tbl.query(h_seqs.array, off, cb.PML_U16, out=(pp.array, pc.array))   # pinned results: the chain-id transport is possible
+    assert np.array_equal(pp.array.astype(np.uint32), want_p) and np.array_equal(pc.array, want_c)
     res = tbl.query_compact(seqs, off)
     pml, cid = cb.compact_expand(res, off, cb.PML_U16)
     assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)

@@ -29,4 +29,4 @@ for _ in range(3):
 ms = b.run(5)
 pml, cid = b.download()
 crc = [zlib.crc32(memoryview(np.ascontiguousarray(pml)).cast("B")), zlib.crc32(memoryview(np.ascontiguousarray(cid)).cast("B"))]
-print(json.dumps({"workload": wl, "lib": os.environ.get("COLBWT_LIB", "default"), "crc32_pml_cid": crc, "ms": ms, "gbases_s": seqs.size / ms / 1e6, "pml_bytes": width, "launches": b.launches}))
+print(json.dumps({"workload": wl, "lib": os.environ.get("COLBWT_LIB", "default"), "crc32_pml_cid": crc, "ms": ms, "gbases_s": seqs.size / ms / 1e6, "pml_bytes": width, "launches": b.launches, "long_reads": b.counters}))

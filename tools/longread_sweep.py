@@ -13,10 +13,14 @@ path, text, ss, meta = bench.build_workload(wl, "cuda:0", False)
 seqs, off = bench.make_reads(wl, text, ss, 0, reads, "cuda:0")
 tbl = cb.ColPml.load(path)
 width = bench.pml_width_for(cb, int(np.diff(off).max()))
-geoms = [(4096, 512), (4096, 256), (2048, 256), (8192, 512), (3072, 384), (4096, 128), (2048, 128)]
+geoms = [None, (4096, 512), (2048, 256), (3072, 384), (1536, 256), (1024, 256), (2048, 512)]   # None = the library's own choice (tasks.h: adapted)
 ref = None
-for chunk, warm in geoms:
-    os.environ["COLBWT_SPLIT_CHUNK"], os.environ["COLBWT_SPLIT_WARM"] = str(chunk), str(warm)
+for g in geoms:
+    chunk, warm = g if g else ("auto", "auto")
+    for k in ("COLBWT_SPLIT_CHUNK", "COLBWT_SPLIT_WARM"):
+        os.environ.pop(k, None)
+    if g:
+        os.environ["COLBWT_SPLIT_CHUNK"], os.environ["COLBWT_SPLIT_WARM"] = str(chunk), str(warm)
     b = tbl.batch(seqs, off, width)
     for _ in range(2):
         b.run(1)
@@ -26,5 +30,5 @@ for chunk, warm in geoms:
         ref = (pml, cid)
     same = bool(np.array_equal(pml, ref[0]) and np.array_equal(cid, ref[1]))
     print(json.dumps({"label": label, "workload": wl, "reads": int(off.size - 1), "chunk": chunk, "warm": warm, "ms": round(ms, 2),
-                      "gbases_s": round(seqs.size / ms / 1e6, 2), "same_output_as_first": same}), flush=True)
+                      "gbases_s": round(seqs.size / ms / 1e6, 2), "same_output_as_first": same, **b.counters}), flush=True)
     b.close()
