@@ -301,15 +301,16 @@ class ColPml:
     __del__ = close
 
 
-def compact_expand(result: np.ndarray, offsets, pml_width: int = PML_U16):
-    """Dense (pml, cid) arrays from a compact result -- host only, no GPU needed."""
+def compact_expand(result: np.ndarray, offsets, pml_width: int = PML_U16, cid_only: bool = False):
+    """Dense (pml, cid) arrays from a compact result -- host only, no GPU needed.  cid_only: rebuild the chain ids alone
+    (returns (None, cid))."""
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     result = np.ascontiguousarray(result, dtype=np.uint8)
     total = int(offsets[-1] - offsets[0])
-    pml = np.empty(total, _PML_DTYPE[pml_width])
-    cid = np.empty(total, np.uint8)
-    _check(_L.colbwt_compact_expand(result.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data, pml_width, cid.ctypes.data),
-           "colbwt_compact_expand")
+    pml = None if cid_only else np.empty(total, _PML_DTYPE[pml_width])
+    cid = np.full(total + 64, 0xEE, np.uint8)[:total]
+    _check(_L.colbwt_compact_expand(result.ctypes.data, offsets.ctypes.data, offsets.size - 1, None if cid_only else pml.ctypes.data, pml_width,
+                                    cid.ctypes.data), "colbwt_compact_expand")
     return pml, cid
 
 

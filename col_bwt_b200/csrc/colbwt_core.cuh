@@ -485,18 +485,22 @@ CB_HD void lane_begin_from_state(Lane<PmlT> &L, const BatchView &bv, const Chunk
     if (PACKED) L.rw = ld_ro(bv.words + k.in_off + ((k.hi - 1) >> 4));
 }
 
-// In-trip resolution (COLBWT_INTRIP=1): a fast-forward neighbour or a reposition target that lies in the SAME 128-byte line
-// as the row just gathered (8 rows of 16 bytes per line; the row array is line-aligned) is read at once -- an L1 hit on the
-// line this lane has just brought in -- instead of costing the lane another trip round the warp loop.  A trip is as long as
-// the slowest of the warp's 32 gathers plus ~170 dependent instructions whatever this lane's own gather cost, so what
-// counts is trips per base (C2: 1.38 -> ~1.1; noisy long reads 1.77 -> ~1.3).  Rows in another line stay a trip of their own.
+// In-trip resolution (template parameter INTRIP): a fast-forward neighbour or a reposition target that lies in the SAME
+// 128-byte line as the row just gathered (8 rows of 16 bytes per line; the row array is line-aligned) is read at once instead
+// of costing the lane another trip round the warp loop: fewer trips per base (C2 1.38 -> ~1.1), but every trip now waits
+// for those dependent loads too, and by the time a warp has all its 32 rows the earliest lines have often left the L1
+// (1024 lanes per SM share 992 lines), so the second load is an L2 access.  Measured (profiles/r2/r2_intrip_*.log): worse
+// wherever the table is L2-resident or DRAM bandwidth is the limit (c2small 110.7 -> 71.8, C2 51.3 -> 46.1, c3small
+// 43.9 -> 36.7 Gbases/s), better only where every gather is a DRAM + TLB miss and a trip is long anyway (c5mid, 4 GB table:
+// 23.1 -> 25.8).  The launcher therefore turns it on for tables of 2 GiB and more only (traverse.cu; COLBWT_INTRIP=0|1 in the
+// environment pins it, -DCOLBWT_INTRIP=1 makes it the default of the host emulation).
 #ifndef COLBWT_INTRIP
 #define COLBWT_INTRIP 0
 #endif
 CB_HD bool same_line(uint32_t a, uint32_t b) { return (a >> 3) == (b >> 3); }
 
 // Advance the lane by one gathered row.  code_lut: 256-entry byte -> {0..3, CODE_OTHER, CODE_ABSENT} (byte reads only).
-template <bool PACKED, bool DEFER = false, typename PmlT>
+template <bool PACKED, bool DEFER = false, bool INTRIP = (COLBWT_INTRIP != 0), typename PmlT>
 CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const BatchView &bv, Row row, const uint8_t *code_lut)
 {
     uint32_t len = row_len(row);
@@ -508,21 +512,19 @@ CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const B
         L.state = LANE_LF;
         return;
     }
-#if COLBWT_INTRIP
-    while (L.off >= len && L.addr + 1 < t.r) {   // fast-forward (LF_table.hpp:256-259)
-        L.off -= len;
-        ++L.addr;
-        if (!same_line(L.addr, L.addr - 1)) return;   // the neighbour starts another line: that is the next trip's gather
-        row = ld_row(t.rows + L.addr);                // same 128-byte line as the row just gathered: an L1 hit, no trip
-        len = row_len(row);
-    }
-#else
-    if (L.off >= len && L.addr + 1 < t.r) {      // fast-forward (LF_table.hpp:256-259)
+    if (INTRIP) {
+        while (L.off >= len && L.addr + 1 < t.r) {   // fast-forward (LF_table.hpp:256-259)
+            L.off -= len;
+            ++L.addr;
+            if (!same_line(L.addr, L.addr - 1)) return;   // the neighbour starts another line: that is the next trip's gather
+            row = ld_row(t.rows + L.addr);                // same 128-byte line as the row just gathered: no trip of its own
+            len = row_len(row);
+        }
+    } else if (L.off >= len && L.addr + 1 < t.r) {   // fast-forward (LF_table.hpp:256-259)
         L.off -= len;
         ++L.addr;
         return;
     }
-#endif
     // settled on (addr, off)
     if (L.slot != NO_SLOT) {
         if (L.j == L.emit_top) bv.start_state[L.slot] = ChainState{L.addr, L.off, L.plen, 0};   // arrival at base hi-1
@@ -586,14 +588,12 @@ CB_HD void lane_step(Lane<PmlT> &L, const Stage &sg, const TableView &t, const B
             found = slow_reposition(t, L.addr, L.off, cbyte, &tgt, &use_pred);
         }
         if (found) {
-#if COLBWT_INTRIP
-            if (same_line(tgt, L.addr)) {        // the target shares the gathered line: jump and LF through it in this trip
+            if (INTRIP && same_line(tgt, L.addr)) {   // the target shares the gathered line: jump and LF through it in this trip
                 const Row tr = ld_row(t.rows + tgt);
                 L.off = row_doff(tr) + (use_pred ? row_len(tr) - 1 : 0);
                 L.addr = tr.dest;
                 return;
             }
-#endif
             L.addr = tgt;
             L.state = use_pred ? LANE_REPOS_PRED : LANE_REPOS_SUCC;
             return;

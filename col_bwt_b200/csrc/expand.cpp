@@ -154,25 +154,51 @@ static void expand_reads_t(const uint32_t *match, const uint32_t *cid_words, con
     }
 }
 
-// Chain ids only (the transport that copies PML as it is): every group of 2048 bases is zeroed and its non-zero ids are
-// dropped in from values[prefix[g] ...]; no read boundary matters.
+// Copy a block that was just built in a small local buffer to its place in a large output array without reading the
+// destination first: non-temporal stores for the 16-byte aligned body (measured on the GPU box's host, 16 cores:
+// 201 GB/s against 90 GB/s for ordinary stores, which fetch every line before overwriting it -- profiles/r2/r2_host_membw.log).
+static inline void stream_out(uint8_t *dst, const uint8_t *src, size_t n)
+{
+#if defined(__x86_64__)
+    size_t head = (size_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    n -= head;
+    const size_t body = n & ~(size_t)15;
+    for (size_t i = 0; i < body; i += 16)
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i)));
+    memcpy(dst + body, src + body, n - body);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
+// Chain ids only (the transport that copies PML as it is): every group of 2048 bases is built in a local buffer -- zeros,
+// then its non-zero ids dropped in from values[prefix[g] ...] -- and streamed out; no read boundary matters.
 void expand_cid_groups(const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, uint64_t n_bases, uint64_t g0, uint64_t g1, uint8_t *cid)
 {
     const uint64_t n_words = (n_bases + 31) / 32;
+    alignas(64) uint8_t buf[COMPACT_GROUP_WORDS * 32];
     for (uint64_t g = g0; g < g1; ++g) {
         const uint64_t w0 = g * COMPACT_GROUP_WORDS, w1 = std::min<uint64_t>(n_words, w0 + COMPACT_GROUP_WORDS);
         const uint64_t b0 = w0 * 32, b1 = std::min<uint64_t>(n_bases, w1 * 32);
-        memset(cid + b0, 0, b1 - b0);
+        memset(buf, 0, sizeof(buf));
         uint64_t k = prefix[g];
         for (uint64_t w = w0; w < w1; ++w) {
             uint32_t bits = cid_words[w];
             while (bits) {
                 const uint32_t b = (uint32_t)__builtin_ctz(bits);
                 bits &= bits - 1;
-                cid[w * 32 + b] = values[k++];
+                buf[(w - w0) * 32 + b] = values[k++];
             }
         }
+        stream_out(cid + b0, buf, (size_t)(b1 - b0));
     }
+#if defined(__x86_64__)
+    _mm_sfence();   // the streamed lines are visible before the caller is told the chunk is complete
+#endif
 }
 
 // Reads [ra, rb) of the segment that starts at read r_first; pml / cid point at the segment's base 0.

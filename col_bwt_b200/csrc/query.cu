@@ -1278,7 +1278,7 @@ extern "C" size_t colbwt_compact_bound(const uint64_t *off, uint64_t n_reads)
 
 extern "C" int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid)
 {
-    if (!result || !off || !pml || !cid) {
+    if (!result || !off || !cid) {
         set_error("colbwt_compact_expand: null argument");
         return COLBWT_ERR_ARG;
     }
@@ -1288,7 +1288,7 @@ extern "C" int colbwt_compact_expand(const void *result, const uint64_t *off, ui
         set_error("colbwt_compact_expand: not a compact result of these %llu reads", (unsigned long long)n_reads);
         return COLBWT_ERR_ARG;
     }
-    if (pml_width != COLBWT_PML_U8 && pml_width != COLBWT_PML_U16 && pml_width != COLBWT_PML_U32) {
+    if (pml && pml_width != COLBWT_PML_U8 && pml_width != COLBWT_PML_U16 && pml_width != COLBWT_PML_U32) {
         set_error("pml_width must be 1, 2 or 4");
         return COLBWT_ERR_ARG;
     }
@@ -1302,6 +1302,15 @@ extern "C" int colbwt_compact_expand(const void *result, const uint64_t *off, ui
             return COLBWT_ERR_ARG;
         }
         if (!sg.n_bases) continue;
+        if (!pml) {   // chain ids only: group by group, no read boundary matters
+            const CompactLayout lay(sg.n_bases);
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, lay.n_groups / 16));
+            pool.parallel_for(T, [&](int t) {
+                expand_cid_groups(reinterpret_cast<const uint32_t *>(buf + sg.cid_off), reinterpret_cast<const uint32_t *>(buf + sg.prefix_off), buf + sg.values_off,
+                                  sg.n_bases, lay.n_groups * (uint64_t)t / (uint64_t)T, lay.n_groups * (uint64_t)(t + 1) / (uint64_t)T, cid + sg.first_base);
+            });
+            continue;
+        }
         const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, sg.n_bases >> 16));
         const std::vector<uint64_t> cut = slice_reads(off, sg.first_read, sg.first_read + sg.n_reads, T);
         std::atomic<bool> too_long{false};

@@ -86,6 +86,26 @@ inline int choose_mode(int rule, uint32_t allowed, const double *rate, int n_mod
     return best;
 }
 
+// Stable order by decreasing work.  A batch of long reads is ~1e6 tasks of 32 bytes and the feeder thread plans every chunk
+// while the GPU waits for the next one: a comparison sort took ~20 ms per 200 k tasks, the counting sort (the key is a length
+// of a few thousand) takes one pass.
+inline void sort_longest_first(std::vector<ChunkTask> &v)
+{
+    if (v.size() < 2) return;
+    uint32_t mx = 0;
+    for (const ChunkTask &t : v) mx = std::max(mx, t.len);
+    if ((uint64_t)mx > 8 * (uint64_t)v.size() + (1u << 16)) {   // few tasks, huge keys: not worth a histogram
+        std::stable_sort(v.begin(), v.end(), [](const ChunkTask &x, const ChunkTask &y) { return x.len > y.len; });
+        return;
+    }
+    std::vector<uint32_t> at((size_t)mx + 2, 0);
+    for (const ChunkTask &t : v) ++at[(size_t)(mx - t.len) + 1];
+    for (size_t i = 1; i < at.size(); ++i) at[i] += at[i - 1];
+    std::vector<ChunkTask> out(v.size());
+    for (const ChunkTask &t : v) out[at[(size_t)(mx - t.len)]++] = t;
+    v.swap(out);
+}
+
 struct TaskPlan {
     std::vector<ChunkTask> tasks;     // scheduling order: packed tasks (longest first), then byte tasks (longest first)
     std::vector<ChunkTask> by_slot;   // chunk tasks of the split reads in slot order
@@ -140,9 +160,8 @@ struct TaskPlan {
         for (const ChainDesc &c : chains)
             for (uint32_t i = 0; i < c.n_chunks; ++i) (c.packed ? p : b).push_back(by_slot[c.first_slot + i]);
         for (size_t i = 0; i < wholes.size(); ++i) (wholes_packed[i] ? p : b).push_back(wholes[i]);
-        auto longer = [](const ChunkTask &x, const ChunkTask &y) { return x.len > y.len; };
-        std::stable_sort(p.begin(), p.end(), longer);
-        std::stable_sort(b.begin(), b.end(), longer);
+        sort_longest_first(p);
+        sort_longest_first(b);
         n_tasks = (uint32_t)p.size();
         n_tasks_b = (uint32_t)b.size();
         tasks = std::move(p);

@@ -20,7 +20,7 @@ namespace colbwt {
 
 constexpr int TRAVERSE_THREADS = 256;
 
-template <bool PACKED, typename PmlT, int CTAS, bool NARROW>
+template <bool PACKED, typename PmlT, int CTAS, bool NARROW, bool INTRIP>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, CTAS)
 k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ code_lut_g, unsigned long long *cursor)
 {
@@ -74,7 +74,7 @@ k_traverse(const TableView t, const BatchView bv, const uint8_t *__restrict__ co
                 lane_step_narrow<PACKED, true>(L, sg, t, bv, w, code_lut);
             } else {
                 const Row row = ld_row(t.rows + L.addr);
-                lane_step<PACKED, true>(L, sg, t, bv, row, code_lut);
+                lane_step<PACKED, true, INTRIP>(L, sg, t, bv, row, code_lut);
             }
         }
         // ---- completed output blocks: the warp writes them together (colbwt_core.cuh: flush_word) -------------------
@@ -183,10 +183,10 @@ static int carveout_percent(size_t smem_per_cta /* dynamic + static */, int ctas
     return (int)(pick >= (size_t)per_sm ? 100 : pick * 100 / (size_t)per_sm);
 }
 
-template <bool PACKED, typename PmlT, bool NARROW>
+template <bool PACKED, typename PmlT, bool NARROW, bool INTRIP>
 static int launch_variant(unsigned grid, size_t smem, const DeviceTable &dt, const BatchView &bv, const uint8_t *lut, unsigned long long *cursor, cudaStream_t stream)
 {
-    auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, NARROW>;
+    auto kern = k_traverse<PACKED, PmlT, TRAVERSE_CTAS, NARROW, INTRIP>;
     static std::atomic<uint64_t> configured{0};   // per instantiation: devices whose function attributes are set
     const uint64_t bit = 1ull << (dt.device & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
@@ -209,8 +209,13 @@ static int launch_one(int sm_count, uint32_t reads, const DeviceTable &dt, const
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)sm_count * TRAVERSE_CTAS));
     const size_t smem = (size_t)TRAVERSE_THREADS * stage_words<PmlT>() * sizeof(uint32_t);
     if (dt.view.hot != nullptr)   // narrow layout, built only when COLBWT_NARROW=1 (index.cu)
-        return launch_variant<PACKED, PmlT, true>(grid, smem, dt, bv, lut, cursor, stream);
-    return launch_variant<PACKED, PmlT, false>(grid, smem, dt, bv, lut, cursor, stream);
+        return launch_variant<PACKED, PmlT, true, false>(grid, smem, dt, bv, lut, cursor, stream);
+    // in-trip resolution of same-line neighbours pays only where every gather is a DRAM + TLB miss (colbwt_core.cuh)
+    const char *env = getenv("COLBWT_INTRIP");   // read per launch: tests switch it
+    const int pinned = env ? atoi(env) : -1;
+    const bool intrip = pinned >= 0 ? pinned != 0 : (uint64_t)dt.view.r * sizeof(Row) >= (2ull << 30);
+    if (intrip) return launch_variant<PACKED, PmlT, false, true>(grid, smem, dt, bv, lut, cursor, stream);
+    return launch_variant<PACKED, PmlT, false, false>(grid, smem, dt, bv, lut, cursor, stream);
 }
 
 int launch_traverse(const DeviceTable &dt, const BatchView &bv, int pml_width, unsigned long long *d_cursors, cudaStream_t stream)

@@ -147,7 +147,7 @@ size_t colbwt_compact_bound(const uint64_t *off, uint64_t n_reads);
 int colbwt_query_compact(colbwt_index *idx, const uint8_t *seqs, const uint64_t *off, uint64_t n_reads,
                          void *result, size_t capacity, size_t *bytes_used);
 /* Host-side: rebuild the dense arrays colbwt_query would have returned (pml_width-byte PML, u8 chain ids) for the
- * same reads.  Runs on the library's host threads; needs no GPU. */
+ * same reads.  Runs on the library's host threads; needs no GPU.  pml may be NULL: only the chain ids are rebuilt. */
 int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_reads, void *pml, int pml_width, uint8_t *cid);
 
 /* Where the last colbwt_query on this index packed the reads into 2 bits per base: 0 on the host, 1 on the device (raw

@@ -80,12 +80,13 @@ class Emu:
         self.tasks = nt.value
         return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]
 
-    def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False, defer=False):
-        """defer: post flush requests and serve them with flush_word, as the warps of k_traverse do."""
+    def query(self, seqs, offsets, pml_width=2, force_bytes=False, narrow=False, defer=False, intrip=False):
+        """defer: post flush requests and serve them with flush_word, as the warps of k_traverse do.
+        intrip: the kernel variant that resolves same-line neighbours inside the trip (implies defer)."""
         seqs = np.ascontiguousarray(seqs, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
         pml = np.zeros(seqs.size + 8, {1: np.uint8, 2: np.uint16, 4: np.uint32}[pml_width])
         cid = np.zeros(seqs.size + 8, np.uint8)
         self.iters = self.L.emu_query(self.h, seqs.ctypes.data, offsets.ctypes.data, offsets.size - 1, pml.ctypes.data,
-                                      pml_width, cid.ctypes.data, int(force_bytes) | (2 if narrow else 0) | (4 if defer else 0))
+                                      pml_width, cid.ctypes.data, int(force_bytes) | (2 if narrow else 0) | (4 if (defer or intrip) else 0) | (8 if intrip else 0))
         return pml[:seqs.size].astype(np.uint32), cid[:seqs.size]

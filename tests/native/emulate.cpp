@@ -249,6 +249,7 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
 {
     const bool narrow = (force_bytes & 2) != 0;
     const bool defer = (force_bytes & 4) != 0;   // bit 2: post flush requests and serve them word by word (flush_word), as the warp does
+    const bool intrip = (force_bytes & 8) != 0;  // bit 3: in-trip resolution of same-line neighbours (the kernel variant for tables >= 2 GiB)
     force_bytes &= 1;
     uint64_t iters = 0;
     uint32_t stage_buf[64] = {0};
@@ -276,7 +277,8 @@ uint64_t emu_query(EmuTable *t, const uint8_t *seqs, const uint64_t *off, uint64
                     else lane_step_narrow<P>(L, sg, t->view, bv, base[L.addr], t->code_lut);
                 } else {
                     if (g_trace_on) g_trace.push_back(L.addr);
-                    if (defer) lane_step<P, true>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
+                    if (intrip) lane_step<P, true, true>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);   // as k_traverse<..., INTRIP> calls it
+                    else if (defer) lane_step<P, true>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
                     else lane_step<P>(L, sg, t->view, bv, ld_row(t->view.rows + L.addr), t->code_lut);
                 }
                 if (L.flush) {   // what k_traverse's warp does after the step, one "thread" at a time

@@ -89,6 +89,8 @@ def test_expand_matches_reference_recurrence(width, seed):
     pml, got_cid = cb.compact_expand(buf, off, width)
     assert np.array_equal(pml.astype(np.uint32), dense_from_match(match, off))
     assert np.array_equal(got_cid, cid)
+    _, only_cid = cb.compact_expand(buf, off, width, cid_only=True)   # the group-wise path the chain-id transport uses (streamed stores)
+    assert np.array_equal(only_cid, cid)
     assert [s["n_reads"] for s in cb.compact_segments(buf)] == [b - a for a, b in zip(cuts[:-1], cuts[1:])]
 
 

@@ -54,6 +54,31 @@ def test_emulated_cooperative_flush(small_index, golden_dir, width, narrow):
         assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
 
 
+@pytest.mark.parametrize("width", [1, 2, 4])
+def test_emulated_in_trip_variant(small_index, golden_dir, width):
+    """k_traverse<..., INTRIP> (launched for tables of 2 GiB and more): fast-forward neighbours and reposition targets in the
+    gathered row's own 128-byte line are resolved inside the trip.  Same results, fewer lane iterations."""
+    orc = oracle.Oracle(small_index["path"])
+    emu = Emu(small_index["cols"])
+    sets = [(small_index["seqs"], small_index["off"])]
+    if width > 1:
+        sets.append(concat_reads(adversarial_reads(small_index["haps"])))
+    for seqs, off in sets:
+        p0, c0 = orc.query_batch(seqs, off)
+        for fb in (False, True):
+            p1, c1 = emu.query(seqs, off, pml_width=width, force_bytes=fb, defer=True)
+            base_iters = emu.iters
+            p2, c2 = emu.query(seqs, off, pml_width=width, force_bytes=fb, intrip=True)
+            assert np.array_equal(p0, p2) and np.array_equal(c0, c2) and np.array_equal(p1, p2)
+            assert emu.iters < base_iters
+    if width > 1:
+        path = os.path.join(golden_dir, "pan4.col_pml")
+        ids, seqs, off = parse_fastx(os.path.join(golden_dir, "pan4_reads.fa"))
+        p0, c0 = oracle.Oracle(path).query_batch(seqs, off)
+        p1, c1 = Emu(cols_from_file(path)).query(seqs, off, pml_width=width, intrip=True)
+        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+
+
 def test_emulated_kernel_logic_on_synthetic(small_index):
     orc = oracle.Oracle(small_index["path"])
     emu = Emu(small_index["cols"])

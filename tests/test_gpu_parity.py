@@ -600,6 +600,30 @@ def test_dense_query_over_compact_transport(cb, small_index, monkeypatch, device
     assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
 
 
+def test_in_trip_kernel_variant(cb, small_index, golden_dir, monkeypatch):
+    """COLBWT_INTRIP=1 forces the kernel variant the launcher picks for tables of 2 GiB and more (same-line neighbours
+    resolved inside the trip): identical results on short, irregular and split long reads, all PML widths."""
+    monkeypatch.setenv("COLBWT_INTRIP", "1")
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    for seqs, off in _compact_cases(small_index):
+        want_p, want_c = orc.query_batch(seqs, off)
+        widths = (cb.PML_U8, cb.PML_U16, cb.PML_U32) if int(np.diff(off).max()) < 256 else (cb.PML_U16, cb.PML_U32)
+        for width in widths:
+            b = tbl.batch(seqs, off, width)
+            b.run(1)
+            pml, cid = b.download()
+            b.close()
+            assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+    monkeypatch.setenv("COLBWT_SPLIT", "1")
+    monkeypatch.setenv("COLBWT_SPLIT_CHUNK", "300")
+    monkeypatch.setenv("COLBWT_SPLIT_WARM", "100")
+    seqs, off = _compact_cases(small_index)[2]
+    want_p, want_c = orc.query_batch(seqs, off)
+    pml, cid = tbl.query(seqs, off, cb.PML_U16)
+    assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
 @pytest.mark.parametrize("device_pack", ["0", "1"])
 def test_dense_query_with_compact_chain_ids(cb, small_index, monkeypatch, device_pack):
     """COLBWT_COMPACT_D2H=2: PML is copied into the caller's pinned array as it is, the chain ids cross the link as bit

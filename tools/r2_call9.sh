@@ -15,3 +15,5 @@ COLBWT_TRACE=1 timeout 600 python bench.py --workload c3 --steps 3 --cpu-seconds
 echo "c3 rc=$?"; grep "colbwt_query\]" gpurun_out/r2_bench_c3_n1b.err | tail -6
 for wl in c3 c5mid c3small; do python tools/kernel_only.py $wl >> gpurun_out/r2_kernels9.log 2>> gpurun_out/r2_kernels9.err; done
 cat gpurun_out/r2_kernels9.log
+python tools/gather_lanes.py 32,96,160,366 > gpurun_out/r2_gather_lanes.log 2>&1
+cat gpurun_out/r2_gather_lanes.log
