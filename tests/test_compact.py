@@ -69,9 +69,54 @@ def build_compact(match: np.ndarray, cid: np.ndarray, off: np.ndarray, cuts) -> 
     return buf
 
 
+def dense_from_match_fast(match: np.ndarray, off: np.ndarray) -> np.ndarray:
+    """Same recurrence, vectorised: distance to the next stop (a mismatch, or the position after the read's last base)."""
+    n = match.size
+    stop = np.full(n + 1, n, np.int64)
+    mis = np.flatnonzero(match == 0)
+    stop[mis] = mis
+    ends = off[1:][np.diff(off) > 0].astype(np.int64)          # position after the last base of every non-empty read
+    is_end = np.zeros(n + 1, bool)
+    is_end[ends] = True
+    # a read end at e stops the runs of the bases left of it, but base e itself (first base of the next read) keeps its own value
+    nxt_mis = np.minimum.accumulate(stop[::-1])[::-1][:n]
+    e_pos = np.where(is_end, np.arange(n + 1), n + 1)
+    nxt_end = np.minimum.accumulate(e_pos[::-1])[::-1]
+    nxt_end = nxt_end[1:][:n]                                   # first read end strictly right of the base
+    return (np.minimum(nxt_mis, nxt_end) - np.arange(n)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("no_avx512", ["0", "1"])
+def test_expand_block_edges_and_long_runs(monkeypatch, no_avx512):
+    """Reads that end exactly on 64-base block edges, runs longer than 65535, empty reads between them; both code paths of
+    expand.cpp (AVX-512 where the CPU has it, and the portable table-driven sweep)."""
+    monkeypatch.setenv("COLBWT_NO_AVX512", no_avx512)
+    rng = np.random.default_rng(11)
+    lens = [64, 64, 128, 1, 63, 0, 0, 65, 70000, 0, 4096, 8192, 191, 1, 1, 62, 100000, 3, 64 * 7, 5]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(off[-1])
+    match = (rng.random(n) < 0.9).astype(np.uint8)
+    match[int(off[8]): int(off[9])] = 1                                   # 70000 matches in a row
+    match[int(off[16]): int(off[16]) + 99000] = 1
+    match[int(off[2]): int(off[3])] = 1
+    cid = np.where(rng.random(n) < 0.5, rng.integers(1, 256, size=n), 0).astype(np.uint8)
+    cid[int(off[10]): int(off[11])] = 7                                   # 4096 non-zero ids in a row (full expand masks)
+    want = dense_from_match_fast(match, off)
+    assert np.array_equal(want[: int(off[8])], dense_from_match(match[: int(off[8])], off[:9]))   # the fast restatement against the loop
+    for cuts in ([0, len(lens)], [0, 3, 4, 9, 17, len(lens)]):
+        buf = build_compact(match, cid, off, cuts)
+        pml, got = cb.compact_expand(buf, off, 4)
+        assert np.array_equal(pml, want) and np.array_equal(got, cid)
+        assert int(pml.max()) >= 99000
+        _, only = cb.compact_expand(buf, off, 4, cid_only=True)
+        assert np.array_equal(only, cid)
+
+
+@pytest.mark.parametrize("no_avx512", ["0", "1"])
 @pytest.mark.parametrize("width", [1, 2, 4])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_expand_matches_reference_recurrence(width, seed):
+def test_expand_matches_reference_recurrence(width, seed, no_avx512, monkeypatch):
+    monkeypatch.setenv("COLBWT_NO_AVX512", no_avx512)
     rng = np.random.default_rng(seed)
     max_len = 250 if width == 1 else 5000
     lens = rng.integers(0, max_len, size=300)
