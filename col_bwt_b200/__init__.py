@@ -301,14 +301,24 @@ class ColPml:
     __del__ = close
 
 
+def _aligned_empty(n: int, dtype, align: int = 64, skew: int = 0) -> np.ndarray:
+    """n elements whose first byte sits `skew` bytes after a multiple of `align` (line-aligned arrays let the expander
+    write whole lines with streaming stores; the skew is for tests of the other path)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.empty(n * item + align + skew + item, np.uint8)
+    start = (-raw.ctypes.data) % align + skew
+    return raw[start: start + n * item].view(dtype)
+
+
 def compact_expand(result: np.ndarray, offsets, pml_width: int = PML_U16, cid_only: bool = False):
     """Dense (pml, cid) arrays from a compact result -- host only, no GPU needed.  cid_only: rebuild the chain ids alone
     (returns (None, cid))."""
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     result = np.ascontiguousarray(result, dtype=np.uint8)
     total = int(offsets[-1] - offsets[0])
-    pml = None if cid_only else np.empty(total, _PML_DTYPE[pml_width])
-    cid = np.full(total + 64, 0xEE, np.uint8)[:total]
+    pml = None if cid_only else _aligned_empty(total, _PML_DTYPE[pml_width])
+    cid = _aligned_empty(total, np.uint8)
+    cid[:] = 0xEE
     _check(_L.colbwt_compact_expand(result.ctypes.data, offsets.ctypes.data, offsets.size - 1, None if cid_only else pml.ctypes.data, pml_width,
                                     cid.ctypes.data), "colbwt_compact_expand")
     return pml, cid

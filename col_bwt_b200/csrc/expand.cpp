@@ -345,6 +345,99 @@ CB_AVX512 static void expand_avx512(const uint32_t *match, const uint32_t *cid_w
     }
 }
 
+// 64 bits of a bit array starting at bit `pos` (any alignment, pos may be negative: bits outside the array read as 0).
+static inline uint64_t bits64_at(const uint32_t *words, uint64_t n_words, int64_t pos)
+{
+    if (pos < 0) return pos <= -64 ? 0 : bits64_at(words, n_words, 0) << (uint64_t)(-pos);
+    const uint64_t w = (uint64_t)pos >> 5, sh = (uint64_t)pos & 31;
+    auto word = [&](uint64_t i) -> uint64_t { return i < n_words ? words[i] : 0; };
+    const uint64_t lo = word(w) | (word(w + 1) << 32);
+    return sh ? (lo >> sh) | (word(w + 2) << (64 - sh)) : lo;
+}
+
+// Same computation with the blocks aligned to the DESTINATION (64 chain-id bytes = one line) instead of to the bit arrays:
+// every full block leaves through one non-temporal 64-byte store per line, no window, no second copy.  Needs the PML
+// array to be line-aligned at the same positions (true for page-aligned caller arrays, pinned ones in particular).
+template <typename T>
+CB_AVX512 static void expand_avx512_direct(const uint32_t *match, const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, uint64_t n_words,
+                                           const uint64_t *off, uint64_t base0, uint64_t ra, uint64_t rb, T *pml, uint8_t *cid)
+{
+    const int64_t S = (int64_t)(off[ra] - base0), E = (int64_t)(off[rb] - base0);
+    if (S >= E) return;
+    const int64_t c0 = (int64_t)((64 - ((uintptr_t)cid & 63)) & 63);             // positions p = c0 (mod 64) start a line of cid
+    const __m512i idx = _mm512_load_si512(K512.idx), ff = _mm512_set1_epi8((char)0xFF);
+    const __m512i idx1 = _mm512_add_epi8(idx, _mm512_set1_epi8(1));
+    const __m512i rest = _mm512_sub_epi8(_mm512_set1_epi8(64), idx);
+    __m512i perm[6];
+    __mmask64 keep[6];
+    for (int t = 0; t < 6; ++t) {
+        perm[t] = _mm512_load_si512(K512.shifted[t]);
+        keep[t] = ~0ull >> (1u << t);
+    }
+    __m512i rest_w[4];                                                             // (64 - lane) widened to T, per part of the block
+    if (sizeof(T) == 2)
+        for (int h = 0; h < 2; ++h) rest_w[h] = _mm512_cvtepu8_epi16(_mm512_extracti64x4_epi64(rest, h));
+    else if (sizeof(T) == 4)
+        for (int h = 0; h < 4; ++h) rest_w[h] = _mm512_cvtepu8_epi32(_mm512_extracti32x4_epi32(rest, h));
+    uint64_t k_end = values_before(cid_words, prefix, (uint64_t)E);
+    uint64_t carry = 0;
+    uint64_t ie = rb;
+    // blocks [B, B + 64) with B = c0 (mod 64), from the one holding E - 1 down to the one holding S (B may be negative)
+    auto floor_block = [&](int64_t x) { const int64_t r = ((x - c0) % 64 + 64) % 64; return x - r; };
+    const int64_t b_top = floor_block(E - 1), b_bot = floor_block(S);
+    for (int64_t B = b_top; B >= b_bot; B -= 64) {
+        const uint64_t a = B < S ? (uint64_t)(S - B) : 0, z = (uint64_t)std::min<int64_t>(64, E - B);   // lanes [a, z) are stored
+        const __mmask64 valid = (z == 64 ? ~0ull : ((1ull << z) - 1)) & ~((1ull << a) - 1);
+        uint64_t last = 0;
+        while (ie > ra) {                                  // read ends inside the block (descending cursor)
+            const int64_t e = (int64_t)(off[ie] - base0);
+            if (e == (int64_t)(off[ie - 1] - base0)) { --ie; continue; }   // empty read
+            if (e - 1 < B) break;
+            last |= 1ull << (uint64_t)(e - 1 - B);
+            --ie;
+        }
+        const __mmask64 mism = ~bits64_at(match, n_words, B);
+        __m512i v = _mm512_mask_blend_epi8(last, ff, idx1);
+        v = _mm512_mask_blend_epi8(mism, v, idx);
+#pragma GCC unroll 6
+        for (int t = 0; t < 6; ++t) v = _mm512_min_epu8(v, _mm512_mask_permutexvar_epi8(ff, keep[t], perm[t], v));
+        const __mmask64 none = _mm512_cmpeq_epi8_mask(v, ff);
+        const __m512i d = _mm512_sub_epi8(v, idx);
+        const uint32_t lane0 = (uint32_t)_mm_cvtsi128_si32(_mm512_castsi512_si128(v)) & 0xFFu;
+        T *pout = pml + B;                                                          // lane j -> pout[j]; never dereferenced outside [a, z)
+        const bool full = valid == ~0ull;
+        if (sizeof(T) == 1) {
+            const __m512i r = _mm512_mask_add_epi8(d, none, rest, _mm512_set1_epi8((char)carry));
+            if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(pout), r);
+            else _mm512_mask_storeu_epi8(pout, valid, r);
+        } else if (sizeof(T) == 2) {
+            const __m512i c16 = _mm512_set1_epi16((short)carry);
+#pragma GCC unroll 2
+            for (int h = 0; h < 2; ++h) {
+                const __m512i r = _mm512_mask_add_epi16(_mm512_cvtepu8_epi16(_mm512_extracti64x4_epi64(d, h)), (__mmask32)(none >> (32 * h)), rest_w[h], c16);
+                if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint16_t *>(pout) + 32 * h), r);
+                else _mm512_mask_storeu_epi16(reinterpret_cast<uint16_t *>(pout) + 32 * h, (__mmask32)(valid >> (32 * h)), r);
+            }
+        } else {
+            const __m512i c32 = _mm512_set1_epi32((int)carry);
+#pragma GCC unroll 4
+            for (int h = 0; h < 4; ++h) {
+                const __m512i r = _mm512_mask_add_epi32(_mm512_cvtepu8_epi32(_mm512_extracti32x4_epi32(d, h)), (__mmask16)(none >> (16 * h)), rest_w[h], c32);
+                if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint32_t *>(pout) + 16 * h), r);
+                else _mm512_mask_storeu_epi32(reinterpret_cast<uint32_t *>(pout) + 16 * h, (__mmask16)(valid >> (16 * h)), r);
+            }
+        }
+        carry = lane0 == 0xFFu ? 64 + carry : lane0;
+        const __mmask64 cm = bits64_at(cid_words, n_words, B) & valid;
+        const uint64_t cnt = (uint64_t)__builtin_popcountll(cm);
+        k_end -= cnt;
+        const __m512i vals = _mm512_maskz_loadu_epi8(cnt == 64 ? ~0ull : ((1ull << cnt) - 1), values + k_end);
+        const __m512i cr = _mm512_maskz_expand_epi8(cm, vals);
+        if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(cid + B), cr);
+        else _mm512_mask_storeu_epi8(cid + B, valid, cr);
+    }
+}
+
 // Chain ids of positions [b0, b1) alone.
 CB_AVX512 static void expand_cid_avx512(const uint32_t *cid_words, const uint32_t *prefix, const uint8_t *values, uint64_t n_words, uint64_t b0, uint64_t b1,
                                         uint8_t *cid)
@@ -396,9 +489,19 @@ void expand_reads(const uint32_t *match, const uint32_t *cid_words, const uint32
     const uint64_t n_words = (off[rb] - base0 + 31) / 32;
 #if defined(__x86_64__)
     if (have_avx512()) {
-        if (pml_width == 1) expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint8_t *)pml, cid);
-        else if (pml_width == 2) expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint16_t *)pml, cid);
-        else expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint32_t *)pml, cid);
+        // lines of the chain-id array and of the PML array start at the same positions: blocks aligned to them, one
+        // streamed store per line; otherwise the windowed variant
+        const uint64_t c0 = (64 - ((uintptr_t)cid & 63)) & 63;
+        const bool direct = (((uintptr_t)pml + c0 * (uint64_t)pml_width) & 63) == 0 && !getenv("COLBWT_EXPAND_WINDOWED");
+        if (direct) {
+            if (pml_width == 1) expand_avx512_direct(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint8_t *)pml, cid);
+            else if (pml_width == 2) expand_avx512_direct(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint16_t *)pml, cid);
+            else expand_avx512_direct(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint32_t *)pml, cid);
+        } else {
+            if (pml_width == 1) expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint8_t *)pml, cid);
+            else if (pml_width == 2) expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint16_t *)pml, cid);
+            else expand_avx512(match, cid_words, prefix, values, n_words, off, base0, ra, rb, (uint32_t *)pml, cid);
+        }
         stores_visible();
         return;
     }

@@ -5,6 +5,7 @@
 // word, base j at bits 2*(j & 15) of word j >> 4.  Any other byte (N, lower case, IUPAC, ...) makes the read
 // "irregular": it is shipped as raw bytes and traversed by the byte kernel, so comparisons stay byte-exact.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -131,10 +132,57 @@ __attribute__((target("avx2"))) static void pack_slice_avx2(const uint8_t *seqs,
 }
 #endif
 
+#if defined(__x86_64__)
+// AVX-512 (F + BW + VL) slice packer: 64 bases per step; the ragged end of a read is a masked load (nothing past the read is
+// touched, masked-off lanes pack as code 0) and a masked store of the words it fills.
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_slice_avx512(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1,
+                                                                                  uint64_t r_base, uint64_t base0, uint32_t *words, uint64_t w,
+                                                                                  ReadMeta *meta, std::vector<uint64_t> &irr)
+{
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i three = _mm512_set1_epi8(3), m4 = _mm512_set1_epi16(0x0401), m16 = _mm512_set1_epi32(0x00100001);
+    for (uint64_t i = r0; i < r1; ++i) {
+        const uint64_t beg = off[i], len = off[i + 1] - beg;
+        const uint8_t *p = seqs + beg;
+        uint32_t *out = words + w;
+        __mmask64 bad = 0;
+        uint64_t j = 0;
+        for (; j + 64 <= len; j += 64) {
+            const __m512i x = _mm512_loadu_si512(p + j);
+            const __m512i code = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+            bad |= _mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(lut, code), x);
+            const __m512i n8 = _mm512_madd_epi16(_mm512_maddubs_epi16(code, m4), m16);   // 4 codes -> the low byte of every dword
+            _mm_storeu_si128(reinterpret_cast<__m128i *>(out + (j >> 4)), _mm512_cvtepi32_epi8(n8));
+        }
+        if (j < len) {
+            const uint64_t rem = len - j;
+            const __mmask64 k = (1ull << rem) - 1;
+            const __m512i x = _mm512_maskz_loadu_epi8(k, p + j);
+            const __m512i code = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+            bad |= _mm512_cmpneq_epi8_mask(_mm512_shuffle_epi8(lut, code), x) & k;
+            const __m512i n8 = _mm512_madd_epi16(_mm512_maddubs_epi16(code, m4), m16);
+            _mm_mask_storeu_epi32(out + (j >> 4), (__mmask8)((1u << ((rem + 15) >> 4)) - 1), _mm512_cvtepi32_epi8(n8));
+        }
+        ReadMeta m{beg - base0, (uint32_t)len, (uint32_t)w};
+        if (bad) {
+            m.len = 0;   // skipped by the packed kernel, shipped as bytes
+            irr.push_back(i);
+        }
+        meta[i - r_base] = m;
+        w += (len + 15) >> 4;
+    }
+}
+#endif
+
 void pack_slice(const uint8_t *seqs, const uint64_t *off, uint64_t r0, uint64_t r1, uint64_t r_base, uint64_t base0,
                 uint64_t seq_end, uint32_t *words, uint64_t w, ReadMeta *meta, std::vector<uint64_t> &irr)
 {
 #if defined(__x86_64__)
+    static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+    if (have_avx512 && !getenv("COLBWT_NO_AVX512")) {
+        pack_slice_avx512(seqs, off, r0, r1, r_base, base0, words, w, meta, irr);
+        return;
+    }
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     if (have_avx2) {
         pack_slice_avx2(seqs, off, r0, r1, r_base, base0, seq_end, words, w, meta, irr);

@@ -136,7 +136,9 @@ static void prepare_reads(const uint8_t *seqs, const uint64_t *off, uint64_t r0,
     const uint64_t n_reads = r1 - r0, base0 = off[r0], n_bases = off[r1] - base0;
     st.n_reads = n_reads;
     st.n_bases = n_bases;
-    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size(), n_bases / 65536 + 1));
+    // four slices per thread: the threads take them from a shared counter, so one that is held up (the copy engines and the
+    // other ranks share the memory system) does not hold up the chunk
+    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, n_bases / 65536 + 1));
     std::vector<uint64_t> cut(T + 1), wcount(T + 1, 0), icount(T + 1, 0), ibases(T + 1, 0);
     std::vector<uint32_t> tmax(T, 0);
     for (int t = 0; t <= T; ++t) {   // split by bases

@@ -86,6 +86,37 @@ def dense_from_match_fast(match: np.ndarray, off: np.ndarray) -> np.ndarray:
     return (np.minimum(nxt_mis, nxt_end) - np.arange(n)).astype(np.uint32)
 
 
+def test_expand_into_unaligned_and_skewed_arrays():
+    """The expander's AVX-512 path writes whole 64-byte lines when the PML and chain-id arrays are line-aligned at the same
+    positions, and goes through a window otherwise: result arrays at odd addresses, and skewed against each other."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 400, size=500)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(off[-1])
+    match = (rng.random(n) < 0.8).astype(np.uint8)
+    cid = np.where(rng.random(n) < 0.2, rng.integers(1, 256, size=n), 0).astype(np.uint8)
+    want = dense_from_match(match, off)
+    buf = build_compact(match, cid, off, [0, 7, 250, 500])
+    for width, dt in ((1, np.uint8), (2, np.uint16), (4, np.uint32)):
+        if width == 1:
+            lens1 = np.minimum(lens, 255)
+            off1 = np.concatenate([[0], np.cumsum(lens1)]).astype(np.uint64)
+            m1, c1 = match[: int(off1[-1])], cid[: int(off1[-1])]
+            cases = (off1, m1, c1, dense_from_match(m1, off1), build_compact(m1, c1, off1, [0, 7, 250, 500]))
+        else:
+            cases = (off, match, cid, want, buf)
+        o, m, c, w, b = cases
+        for skew_p, skew_c in ((0, 0), (width, 1), (0, 16), (3 * width, 3), (32, 0)):
+            pml = cb._aligned_empty(int(o[-1]), dt, skew=skew_p)
+            out_c = cb._aligned_empty(int(o[-1]), np.uint8, skew=skew_c)
+            pml[:] = 0xAB
+            out_c[:] = 0xEE
+            rc = cb._L.colbwt_compact_expand(b.ctypes.data, o.ctypes.data, o.size - 1, pml.ctypes.data, width, out_c.ctypes.data)
+            assert rc == 0
+            assert np.array_equal(pml.astype(np.uint32), w) and np.array_equal(out_c, c), (width, skew_p, skew_c)
+
+
 @pytest.mark.parametrize("no_avx512", ["0", "1"])
 def test_expand_block_edges_and_long_runs(monkeypatch, no_avx512):
     """Reads that end exactly on 64-base block edges, runs longer than 65535, empty reads between them; both code paths of
