@@ -35,6 +35,9 @@ public:
     // One job at a time: the job lives in shared fields (fn_, n_tasks_, next_, pending_, epoch_), and the pool is shared by
     // every index and every calling thread of the process (colbwt_query on two indexes, colbwt_batch_upload next to a query,
     // the per-device feeder threads), so callers queue on caller_m_ for the whole parallel_for.
+    // A chunk is packed and expanded in a few parallel_for calls of ~1 ms each, so how fast the workers pick a job up counts:
+    // they spin on the epoch for ~100 us after finishing one before they go to sleep on the condition variable, and the caller
+    // spins as long for the last of them to finish.
     void parallel_for(int n_tasks, const std::function<void(int)> &fn)
     {
         if (n_tasks <= 1 || workers_.empty()) {
@@ -47,17 +50,27 @@ public:
             fn_ = &fn;
             n_tasks_ = n_tasks;
             next_.store(0);
-            pending_ = (int)workers_.size();
-            ++epoch_;
+            pending_.store((int)workers_.size());
+            epoch_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         run_tasks();
-        std::unique_lock<std::mutex> g(m_);
-        done_cv_.wait(g, [&] { return pending_ == 0; });
+        for (int spin = 0; spin < SPINS && pending_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
+        if (pending_.load(std::memory_order_acquire) != 0) {
+            std::unique_lock<std::mutex> g(m_);
+            done_cv_.wait(g, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+        }
         fn_ = nullptr;
     }
 
 private:
+    static constexpr int SPINS = 2000;
+    static inline void cpu_relax()
+    {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
     Pool()
     {
         int n = (int)std::thread::hardware_concurrency();
@@ -71,7 +84,7 @@ private:
         {
             std::lock_guard<std::mutex> g(m_);
             stop_ = true;
-            ++epoch_;
+            epoch_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto &t : workers_) t.join();
@@ -88,16 +101,17 @@ private:
     {
         uint64_t seen = 0;
         for (;;) {
-            {
+            for (int spin = 0; spin < SPINS && epoch_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
+            if (epoch_.load(std::memory_order_acquire) == seen) {
                 std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [&] { return epoch_ != seen; });
-                seen = epoch_;
-                if (stop_) return;
+                cv_.wait(g, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
             }
+            seen = epoch_.load(std::memory_order_acquire);
+            if (stop_) return;
             run_tasks();
-            {
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0) done_cv_.notify_one();
+                done_cv_.notify_one();
             }
         }
     }
@@ -106,10 +120,10 @@ private:
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)> *fn_ = nullptr;
-    std::atomic<int> next_{0};
-    int n_tasks_ = 0, pending_ = 0;
-    uint64_t epoch_ = 0;
-    bool stop_ = false;
+    std::atomic<int> next_{0}, pending_{0};
+    int n_tasks_ = 0;
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<bool> stop_{false};
 };
 
 // ---------------------------------------------------------------------------------------------------------
