@@ -1088,7 +1088,12 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     pin_field("COLBWT_DEVICE_PACK", true);
     pin_field("COLBWT_COMPACT_D2H", false);
     double *rates = idx->mode_rate[compact_api ? 1 : 0];
-    int rule = (Pool::get().size() < 8) ? 1 : 0;
+    // Starting guess.  Plenty of host threads (one process, one GPU): pack on the host, copy the dense arrays.  Few threads per
+    // process (one rank per GPU on a shared host: 4 each on the 8-GPU box) means a link shared with the other ranks as well:
+    // fewest bytes and least host work first -- raw reads packed on the device, compact transport (8 ranks on C2: 12.3
+    // Gbases/s per rank that way against 7.5-10.3 for the other modes, profiles/r2/r2_bench_c2_n8_trace.log).  With all ranks
+    // trying modes at the same time a single sample is noisy, so the rule keeps its place unless clearly beaten.
+    int rule = (Pool::get().size() < 8) ? 3 : 0;
     const int mode = choose_mode(rule, allowed, rates, N_MODES, large_call);   // tasks.h
     const bool device_pack = (mode & 1) != 0;
     const OutKind kind = compact_api ? OUT_COMPACT : ((mode >> 1) == 1 ? OUT_DENSE_VIA_COMPACT : (mode >> 1) == 2 ? OUT_DENSE_CID_COMPACT : OUT_DENSE);

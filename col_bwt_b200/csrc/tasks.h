@@ -66,8 +66,11 @@ struct SplitParams {
 inline int choose_mode(int rule, uint32_t allowed, const double *rate, int n_modes, bool large_call)
 {
     if (!(allowed & (1u << rule))) {
-        // the rule is not available to this call: keep what it can of the rule (its low bits), else the lowest allowed mode
+        // the rule is not available to this call: keep what it can of the rule -- its transport (mode >> 1) first, then its
+        // packing bit (mode & 1) -- else the lowest allowed mode
         int pick = -1;
+        for (int m = 0; m < n_modes && pick < 0; ++m)
+            if ((allowed & (1u << m)) && (m >> 1) == (rule >> 1)) pick = m;
         for (int m = 0; m < n_modes && pick < 0; ++m)
             if ((allowed & (1u << m)) && (m & 1) == (rule & 1)) pick = m;
         for (int m = 0; m < n_modes && pick < 0; ++m)

@@ -325,3 +325,14 @@ def test_mode_choice_is_measured_then_kept():
     assert f(1, [0, 0, 0, 0], allowed=0b0101) == 0
     assert f(1, [9e9, 0, 0, 0], allowed=0b0101) == 2
     assert f(1, [9e9, 0, 12e9, 0], allowed=0b0101) == 2 and f(1, [9e9, 0, 9.2e9, 0], allowed=0b0101) == 0
+
+    # six modes (mode = packing bit + 2 x transport); few host threads start from mode 3 = device packing + compact transport;
+    # a call that cannot pack on the device (long reads, pageable input) keeps the rule's TRANSPORT: mode 2
+    def g(rule, rates, allowed):
+        arr = (C.c_double * 6)(*rates)
+        return L.emu_choose_mode(rule, allowed, arr, 6, 1)
+    assert g(3, [0] * 6, 0b111111) == 3
+    assert g(3, [0] * 6, 0b010101) == 2
+    assert g(3, [0, 0, 8e9, 0, 0, 0], 0b010101) == 0              # then the other allowed modes, once each
+    assert g(3, [7e9, 0, 8e9, 0, 0, 0], 0b010101) == 4
+    assert g(3, [7e9, 0, 8e9, 0, 8.3e9, 0], 0b010101) == 2        # 4 % better is not enough to displace the rule's stand-in
