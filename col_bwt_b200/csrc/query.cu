@@ -35,9 +35,7 @@ public:
     // One job at a time: the job lives in shared fields (fn_, n_tasks_, next_, pending_, epoch_), and the pool is shared by
     // every index and every calling thread of the process (colbwt_query on two indexes, colbwt_batch_upload next to a query,
     // the per-device feeder threads), so callers queue on caller_m_ for the whole parallel_for.
-    // A chunk is packed and expanded in a few parallel_for calls of ~1 ms each, so how fast the workers pick a job up counts:
-    // they spin on the epoch for ~100 us after finishing one before they go to sleep on the condition variable, and the caller
-    // spins as long for the last of them to finish.
+    // Workers sleep on a condition variable between jobs (optionally after spinning on the epoch for a while, see SPINS).
     void parallel_for(int n_tasks, const std::function<void(int)> &fn)
     {
         if (n_tasks <= 1 || workers_.empty()) {
@@ -64,7 +62,17 @@ public:
     }
 
 private:
-    static constexpr int SPINS = 2000;
+    // Spinning between jobs (COLBWT_POOL_SPIN = iterations of `pause`, ~50 ns each) is OFF by default: on one GPU with 16 cores
+    // it changed nothing (29.1 / 28.9 against 29.5 / 28.9 Gbases/s end to end, profiles/r2/r2_spin*.json), and with one rank
+    // per GPU on a fully subscribed host (8 ranks x 4 threads + their CUDA and Python threads on 32 vCPUs) the spinners take
+    // the cores the other ranks' packers need: every host-heavy mode ran at half its rate in the 8-rank run that had them
+    // (profiles/r2/SUMMARY.md section 6).
+    const int SPINS = spin_budget();
+    static int spin_budget()
+    {
+        if (const char *e = getenv("COLBWT_POOL_SPIN")) return std::max(0, atoi(e));
+        return 0;
+    }
     static inline void cpu_relax()
     {
 #if defined(__x86_64__)
