@@ -672,10 +672,7 @@ static int get_pipeline(colbwt_index *idx, uint64_t chunk_reads, uint64_t chunk_
     return COLBWT_OK;
 }
 
-// ---- chunk planning -------------------------------------------------------------------------------------------
-struct Chunk { uint64_t r0, r1; };
-struct Geometry { uint64_t chunk_bases = 0, chunk_reads = 0, grow_bases = 0, min_reads = 0; uint32_t max_len = 0; };
-
+// ---- chunk planning: tasks.h (Chunk, Geometry, chunk_geometry, plan_chunks) --------------------------------------------
 // One pass over the offsets (longest read, sanity), shared among the packing threads: 10 M reads are 80 MB.
 static int scan_offsets(const uint64_t *off, uint64_t n_reads, uint32_t *max_len_out)
 {
@@ -703,57 +700,6 @@ static int scan_offsets(const uint64_t *off, uint64_t n_reads, uint32_t *max_len
     }
     *max_len_out = (uint32_t)mx;
     return COLBWT_OK;
-}
-
-// staged_bytes_per_base: bytes of pinned staging a base of output needs when the destination cannot be DMA-ed into
-// directly (0 otherwise); bounds the chunk so that one slot's staging stays under 256 MB.
-static Geometry chunk_geometry(uint64_t total_bases, uint64_t n_reads, uint32_t max_len, uint64_t staged_bytes_per_base)
-{
-    Geometry g;
-    g.max_len = max_len;
-    uint64_t chunk_bases = 96ull << 20;   // measured on C2 (profiles/r1/e2e_chunk_sweep.log): 16/24/32/48/96/128/192 M -> 83.6/85.0/81.1/76.3/71.8-73.2/72.0/73.1 ms
-    const char *env = getenv("COLBWT_CHUNK_BASES");
-    if (env) chunk_bases = std::max<uint64_t>(1024, strtoull(env, nullptr, 10));
-    // Long reads: a chunk must still hold enough reads to occupy the lanes (a lane works on one read or chunk task at a
-    // time and several chunks are in flight), so a chunk that reaches chunk_bases with fewer than 32 Ki reads keeps growing,
-    // up to 512 Mbases.  Decided chunk by chunk (plan_chunks), not from the batch's mean read length: in a mixed batch
-    // (configs[4]: 12.4 M short reads followed by 125 k long ones) the long reads would otherwise be cut into 96-Mbase
-    // chunks of 9.6 k reads each, every one of them as slow as its longest serial chain.
-    uint64_t grow_bases = env ? chunk_bases : (512ull << 20);
-    if (staged_bytes_per_base && !env) {
-        chunk_bases = std::min<uint64_t>(chunk_bases, (256ull << 20) / staged_bytes_per_base);
-        grow_bases = std::min<uint64_t>(grow_bases, (256ull << 20) / staged_bytes_per_base);
-    }
-    chunk_bases = std::max<uint64_t>(chunk_bases, max_len);
-    chunk_bases = std::min<uint64_t>(chunk_bases, std::max<uint64_t>(total_bases, 16));
-    g.chunk_bases = chunk_bases;
-    g.grow_bases = std::min<uint64_t>(std::max(grow_bases, chunk_bases), std::max<uint64_t>(total_bases, 16));
-    g.min_reads = 32768;
-    // a chunk also ends after chunk_bases/32 reads, which bounds the meta staging (16 B per read) for very short reads
-    g.chunk_reads = std::min<uint64_t>(std::max<uint64_t>(chunk_bases / 32, 1024), n_reads);
-    return g;
-}
-
-// Cuts the batch into chunks and leaves the capacities the staging needs (largest chunk in bases and in reads) in g.
-static void plan_chunks(const uint64_t *off, uint64_t n_reads, Geometry &g, std::vector<Chunk> &chunks)
-{
-    chunks.clear();
-    uint64_t cap_bases = 16, cap_reads = 1;
-    for (uint64_t r0 = 0; r0 < n_reads;) {   // at most chunk_bases bases (grow_bases while short of min_reads reads) and chunk_reads reads, at least one read
-        uint64_t r1 = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + g.chunk_bases) - off) - 1;
-        if (r1 - r0 < g.min_reads && g.grow_bases > g.chunk_bases) {
-            const uint64_t far = (uint64_t)(std::upper_bound(off + r0, off + n_reads + 1, off[r0] + g.grow_bases) - off) - 1;
-            r1 = std::max(r1, std::min(far, r0 + g.min_reads));
-        }
-        r1 = std::min(r1, r0 + g.chunk_reads);
-        if (r1 <= r0) r1 = r0 + 1;
-        chunks.push_back(Chunk{r0, r1});
-        cap_bases = std::max(cap_bases, off[r1] - off[r0]);
-        cap_reads = std::max(cap_reads, r1 - r0);
-        r0 = r1;
-    }
-    g.chunk_bases = cap_bases;
-    g.chunk_reads = cap_reads;
 }
 
 // ---- one call ---------------------------------------------------------------------------------------------------

@@ -224,6 +224,22 @@ void emu_adapted(uint64_t total_bases, uint64_t lanes, uint32_t *out)
     out[3] = sp.whole_min();
 }
 
+// Streaming chunks of colbwt_query (tasks.h: chunk_geometry + plan_chunks): writes r0 of every chunk (and n_reads at the end)
+// to out; returns the number of chunks.  caps[0..1] = largest chunk in bases / in reads (what the staging is sized for).
+uint64_t emu_plan_chunks(const uint64_t *off, uint64_t n_reads, uint64_t staged_bytes_per_base, uint64_t *out, uint64_t cap, uint64_t *caps)
+{
+    uint64_t max_len = 0;
+    for (uint64_t i = 0; i < n_reads; ++i) max_len = std::max(max_len, off[i + 1] - off[i]);
+    Geometry g = chunk_geometry(off[n_reads] - off[0], n_reads, (uint32_t)max_len, staged_bytes_per_base);
+    std::vector<Chunk> chunks;
+    plan_chunks(off, n_reads, g, chunks);
+    for (size_t i = 0; i < chunks.size() && i < cap; ++i) out[i] = chunks[i].r0;
+    if (chunks.size() < cap) out[chunks.size()] = chunks.empty() ? 0 : chunks.back().r1;
+    caps[0] = g.chunk_bases;
+    caps[1] = g.chunk_reads;
+    return chunks.size();
+}
+
 int emu_choose_mode(int rule, uint32_t allowed, const double *rate, int n_modes, int large_call)
 {
     return choose_mode(rule, allowed, rate, n_modes, large_call != 0);

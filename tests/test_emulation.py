@@ -293,6 +293,43 @@ def test_chunk_geometry_follows_the_batch():
     assert c % 256 == 0 and 2048 <= c <= 2560 and w == 256 and m == c + c // 2
 
 
+def test_streaming_chunks_follow_the_reads(monkeypatch):
+    """tasks.h: chunk_geometry + plan_chunks -- 96-Mbase chunks for short reads; where a chunk would hold fewer than 32 Ki reads
+    (long reads, also behind millions of short ones in the same batch) it grows, up to 512 Mbases; chunks tile the batch."""
+    import ctypes as C
+    from emu import SO, build
+    build()
+    L = C.CDLL(SO)
+    L.emu_plan_chunks.restype = C.c_uint64
+    L.emu_plan_chunks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    monkeypatch.delenv("COLBWT_CHUNK_BASES", raising=False)
+
+    def plan(lens, staged=0):
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        out, caps = np.zeros(4096, np.uint64), np.zeros(2, np.uint64)
+        n = int(L.emu_plan_chunks(off.ctypes.data, off.size - 1, staged, out.ctypes.data, out.size, caps.ctypes.data))
+        cuts = out[: n + 1].astype(np.int64)
+        assert cuts[0] == 0 and cuts[-1] == off.size - 1 and (np.diff(cuts) > 0).all()      # tiles the batch, no empty chunk
+        bases = np.diff(off[cuts].astype(np.int64))
+        assert bases.max() == int(caps[0]) and np.diff(cuts).max() == int(caps[1])
+        return cuts, bases
+    M = 1 << 20
+    cuts, bases = plan(np.full(3_000_000, 150))                              # short reads: 96 Mbases per chunk
+    assert len(bases) == 5 and (bases[:-1] <= 96 * M).all() and (bases[:-1] > 96 * M - 150).all()
+    cuts, bases = plan(np.full(100_000, 10_000))                             # long reads: 32 Ki reads per chunk
+    assert (np.diff(cuts)[:-1] == 32768).all() and bases.max() == 327_680_000
+    cuts, bases = plan(np.full(5_000, 200_000))                              # very long reads: capped at 512 Mbases
+    assert bases.max() <= 512 * M and bases[:-1].min() > 512 * M - 200_000
+    lens = np.concatenate([np.full(2_000_000, 150), np.full(40_000, 10_000)])   # mixed batch (configs[4]): the long tail gets long-read chunks
+    cuts, bases = plan(lens)
+    assert (bases[:2] <= 96 * M).all() and bases[-2:].sum() > 300 * M and len(bases) <= 6
+    cuts, bases = plan(np.full(100_000, 10_000), staged=5)                   # pageable results: staging bounded to 256 MB per slot
+    assert bases.max() * 5 <= 256 * M
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "50000")                        # tests pin tiny chunks: no growth
+    cuts, bases = plan(np.full(1000, 3000))
+    assert bases.max() <= 51_000 and len(bases) >= 59
+
+
 def test_mode_choice_is_measured_then_kept():
     """tasks.h: choose_mode -- the rule first, every other allowed mode once, then the fastest (the rule keeps its place
     within 5 %).  Modes of colbwt_query: bit 0 = reads packed on the device, bit 1 = compact transport."""
