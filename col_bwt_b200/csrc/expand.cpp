@@ -350,6 +350,11 @@ static inline uint64_t bits64_at(const uint32_t *words, uint64_t n_words, int64_
 {
     if (pos < 0) return pos <= -64 ? 0 : bits64_at(words, n_words, 0) << (uint64_t)(-pos);
     const uint64_t w = (uint64_t)pos >> 5, sh = (uint64_t)pos & 31;
+    if (w + 3 <= n_words) {                                // interior: three words, no bounds to check
+        uint64_t lo;
+        memcpy(&lo, words + w, 8);
+        return sh ? (lo >> sh) | ((uint64_t)words[w + 2] << (64 - sh)) : lo;
+    }
     auto word = [&](uint64_t i) -> uint64_t { return i < n_words ? words[i] : 0; };
     const uint64_t lo = word(w) | (word(w + 1) << 32);
     return sh ? (lo >> sh) | (word(w + 2) << (64 - sh)) : lo;
@@ -385,56 +390,71 @@ CB_AVX512 static void expand_avx512_direct(const uint32_t *match, const uint32_t
     // blocks [B, B + 64) with B = c0 (mod 64), from the one holding E - 1 down to the one holding S (B may be negative)
     auto floor_block = [&](int64_t x) { const int64_t r = ((x - c0) % 64 + 64) % 64; return x - r; };
     const int64_t b_top = floor_block(E - 1), b_bot = floor_block(S);
-    for (int64_t B = b_top; B >= b_bot; B -= 64) {
-        const uint64_t a = B < S ? (uint64_t)(S - B) : 0, z = (uint64_t)std::min<int64_t>(64, E - B);   // lanes [a, z) are stored
-        const __mmask64 valid = (z == 64 ? ~0ull : ((1ull << z) - 1)) & ~((1ull << a) - 1);
-        uint64_t last = 0;
-        while (ie > ra) {                                  // read ends inside the block (descending cursor)
-            const int64_t e = (int64_t)(off[ie] - base0);
-            if (e == (int64_t)(off[ie - 1] - base0)) { --ie; continue; }   // empty read
-            if (e - 1 < B) break;
-            last |= 1ull << (uint64_t)(e - 1 - B);
-            --ie;
-        }
-        const __mmask64 mism = ~bits64_at(match, n_words, B);
-        __m512i v = _mm512_mask_blend_epi8(last, ff, idx1);
-        v = _mm512_mask_blend_epi8(mism, v, idx);
-#pragma GCC unroll 6
-        for (int t = 0; t < 6; ++t) v = _mm512_min_epu8(v, _mm512_mask_permutexvar_epi8(ff, keep[t], perm[t], v));
-        const __mmask64 none = _mm512_cmpeq_epi8_mask(v, ff);
-        const __m512i d = _mm512_sub_epi8(v, idx);
-        const uint32_t lane0 = (uint32_t)_mm_cvtsi128_si32(_mm512_castsi512_si128(v)) & 0xFFu;
-        T *pout = pml + B;                                                          // lane j -> pout[j]; never dereferenced outside [a, z)
-        const bool full = valid == ~0ull;
-        if (sizeof(T) == 1) {
-            const __m512i r = _mm512_mask_add_epi8(d, none, rest, _mm512_set1_epi8((char)carry));
-            if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(pout), r);
-            else _mm512_mask_storeu_epi8(pout, valid, r);
-        } else if (sizeof(T) == 2) {
-            const __m512i c16 = _mm512_set1_epi16((short)carry);
+    // two blocks per trip: their suffix-minimum scans are independent dependency chains of ~25 cycles each
+    for (int64_t Bp = b_top; Bp >= b_bot; Bp -= 128) {
+        const int nb = Bp - 64 >= b_bot ? 2 : 1;
+        __m512i v[2] = {ff, ff};
 #pragma GCC unroll 2
-            for (int h = 0; h < 2; ++h) {
-                const __m512i r = _mm512_mask_add_epi16(_mm512_cvtepu8_epi16(_mm512_extracti64x4_epi64(d, h)), (__mmask32)(none >> (32 * h)), rest_w[h], c16);
-                if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint16_t *>(pout) + 32 * h), r);
-                else _mm512_mask_storeu_epi16(reinterpret_cast<uint16_t *>(pout) + 32 * h, (__mmask32)(valid >> (32 * h)), r);
+        for (int u = 0; u < 2; ++u) {
+            if (u >= nb) break;
+            const int64_t B = Bp - 64 * u;
+            uint64_t last = 0;
+            while (ie > ra) {                              // read ends inside the block (descending cursor)
+                const int64_t e = (int64_t)(off[ie] - base0);
+                if (e == (int64_t)(off[ie - 1] - base0)) { --ie; continue; }   // empty read
+                if (e - 1 < B) break;
+                last |= 1ull << (uint64_t)(e - 1 - B);
+                --ie;
             }
-        } else {
-            const __m512i c32 = _mm512_set1_epi32((int)carry);
-#pragma GCC unroll 4
-            for (int h = 0; h < 4; ++h) {
-                const __m512i r = _mm512_mask_add_epi32(_mm512_cvtepu8_epi32(_mm512_extracti32x4_epi32(d, h)), (__mmask16)(none >> (16 * h)), rest_w[h], c32);
-                if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint32_t *>(pout) + 16 * h), r);
-                else _mm512_mask_storeu_epi32(reinterpret_cast<uint32_t *>(pout) + 16 * h, (__mmask16)(valid >> (16 * h)), r);
-            }
+            const __mmask64 mism = ~bits64_at(match, n_words, B);
+            v[u] = _mm512_mask_blend_epi8(mism, _mm512_mask_blend_epi8(last, ff, idx1), idx);
         }
-        carry = lane0 == 0xFFu ? 64 + carry : lane0;
-        const __mmask64 cm = bits64_at(cid_words, n_words, B) & valid;
-        const uint64_t cnt = (uint64_t)__builtin_popcountll(cm);
-        k_end -= cnt;
-        const __m512i vals = _mm512_maskz_loadu_epi8(cnt == 64 ? ~0ull : ((1ull << cnt) - 1), values + k_end);
-        const __m512i cr = _mm512_maskz_expand_epi8(cm, vals);
-        if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(cid + B), cr);
-        else _mm512_mask_storeu_epi8(cid + B, valid, cr);
+#pragma GCC unroll 6
+        for (int t = 0; t < 6; ++t) {
+            v[0] = _mm512_min_epu8(v[0], _mm512_mask_permutexvar_epi8(ff, keep[t], perm[t], v[0]));
+            v[1] = _mm512_min_epu8(v[1], _mm512_mask_permutexvar_epi8(ff, keep[t], perm[t], v[1]));
+        }
+#pragma GCC unroll 2
+        for (int u = 0; u < 2; ++u) {
+            if (u >= nb) break;
+            const int64_t B = Bp - 64 * u;
+            const uint64_t a = B < S ? (uint64_t)(S - B) : 0, z = (uint64_t)std::min<int64_t>(64, E - B);   // lanes [a, z) are stored
+            const __mmask64 valid = (z == 64 ? ~0ull : ((1ull << z) - 1)) & ~((1ull << a) - 1);
+            const __mmask64 none = _mm512_cmpeq_epi8_mask(v[u], ff);
+            const __m512i d = _mm512_sub_epi8(v[u], idx);
+            const uint32_t lane0 = (uint32_t)_mm_cvtsi128_si32(_mm512_castsi512_si128(v[u])) & 0xFFu;
+            T *pout = pml + B;                                                      // lane j -> pout[j]; never dereferenced outside [a, z)
+            const bool full = valid == ~0ull;
+            if (sizeof(T) == 1) {
+                const __m512i r = _mm512_mask_add_epi8(d, none, rest, _mm512_set1_epi8((char)carry));
+                if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(pout), r);
+                else _mm512_mask_storeu_epi8(pout, valid, r);
+            } else if (sizeof(T) == 2) {
+                const __m512i c16 = _mm512_set1_epi16((short)carry);
+#pragma GCC unroll 2
+                for (int h = 0; h < 2; ++h) {
+                    const __m512i r = _mm512_mask_add_epi16(_mm512_cvtepu8_epi16(_mm512_extracti64x4_epi64(d, h)), (__mmask32)(none >> (32 * h)), rest_w[h], c16);
+                    if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint16_t *>(pout) + 32 * h), r);
+                    else _mm512_mask_storeu_epi16(reinterpret_cast<uint16_t *>(pout) + 32 * h, (__mmask32)(valid >> (32 * h)), r);
+                }
+            } else {
+                const __m512i c32 = _mm512_set1_epi32((int)carry);
+#pragma GCC unroll 4
+                for (int h = 0; h < 4; ++h) {
+                    const __m512i r = _mm512_mask_add_epi32(_mm512_cvtepu8_epi32(_mm512_extracti32x4_epi32(d, h)), (__mmask16)(none >> (16 * h)), rest_w[h], c32);
+                    if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(reinterpret_cast<uint32_t *>(pout) + 16 * h), r);
+                    else _mm512_mask_storeu_epi32(reinterpret_cast<uint32_t *>(pout) + 16 * h, (__mmask16)(valid >> (16 * h)), r);
+                }
+            }
+            carry = lane0 == 0xFFu ? 64 + carry : lane0;
+            const __mmask64 cm = bits64_at(cid_words, n_words, B) & valid;
+            const uint64_t cnt = (uint64_t)__builtin_popcountll(cm);
+            k_end -= cnt;
+            const __m512i vals = _mm512_maskz_loadu_epi8(cnt == 64 ? ~0ull : ((1ull << cnt) - 1), values + k_end);
+            const __m512i cr = _mm512_maskz_expand_epi8(cm, vals);
+            if (full) _mm512_stream_si512(reinterpret_cast<__m512i *>(cid + B), cr);
+            else _mm512_mask_storeu_epi8(cid + B, valid, cr);
+        }
     }
 }
 
