@@ -339,6 +339,7 @@ def test_synthetic_move_table_from_rows(cb):
 
 @pytest.mark.parametrize("split_env", [{"COLBWT_SPLIT": "1", "COLBWT_SPLIT_CHUNK": "64", "COLBWT_SPLIT_WARM": "16", "COLBWT_SPLIT_MIN": "128"},
                                        {"COLBWT_SPLIT": "1", "COLBWT_SPLIT_CHUNK": "256", "COLBWT_SPLIT_WARM": "256", "COLBWT_SPLIT_MIN": "512"},
+                                       {"COLBWT_SPLIT": "1", "COLBWT_SPLIT_CHUNK": "128", "COLBWT_SPLIT_WARM": "0", "COLBWT_SPLIT_MIN": "256"},
                                        {"COLBWT_SPLIT": "1"}])
 def test_long_reads_split_into_chunk_tasks(cb, small_index, monkeypatch, split_env):
     """The long-read path (speculative chunk tasks + k_fixup) on the GPU: tiny chunks with a short warm-up force many
@@ -362,6 +363,14 @@ def test_long_reads_split_into_chunk_tasks(cb, small_index, monkeypatch, split_e
     b.run(2)
     p2, c2 = b.download()
     assert np.array_equal(p2, want_p) and np.array_equal(c2, want_c)
+    # bookkeeping of the long-read path (colbwt_batch_counters): the cut reads, their chunk tasks, the whole reads scheduled
+    # among them, and how many chunks the last traversal had to redo because their speculative start had not converged
+    k = b.counters
+    assert k["split_reads"] >= 40 and k["chunk_tasks"] >= 2 * k["split_reads"] and k["scheduled"] >= k["chunk_tasks"]
+    if split_env.get("COLBWT_SPLIT_WARM") == "0":
+        assert k["retraversed"] > 0.5 * (k["chunk_tasks"] - k["split_reads"])    # no warm-up: nearly every speculative chunk is redone
+    else:
+        assert k["retraversed"] <= k["chunk_tasks"] - k["split_reads"]
 
 
 def test_device_side_packing_with_pinned_input(cb, small_index, monkeypatch):
