@@ -390,22 +390,30 @@ CB_AVX512 static void expand_avx512_direct(const uint32_t *match, const uint32_t
     // blocks [B, B + 64) with B = c0 (mod 64), from the one holding E - 1 down to the one holding S (B may be negative)
     auto floor_block = [&](int64_t x) { const int64_t r = ((x - c0) % 64 + 64) % 64; return x - r; };
     const int64_t b_top = floor_block(E - 1), b_bot = floor_block(S);
-    // two blocks per trip: their suffix-minimum scans are independent dependency chains of ~25 cycles each
+    // Read-end bits are laid out for a span of 64 blocks at a time (one short loop over the reads that end in the span: a
+    // per-block search for them costs a fifth of the whole expansion in mispredicted branches); then two blocks per trip:
+    // their suffix-minimum scans are independent dependency chains of ~25 cycles each.
+    constexpr int64_t SPAN_BLOCKS = 64;
+    uint64_t ends[SPAN_BLOCKS];
+    int64_t span_bot = b_top + 64;                           // blocks >= span_bot have their end bits consumed
     for (int64_t Bp = b_top; Bp >= b_bot; Bp -= 128) {
         const int nb = Bp - 64 >= b_bot ? 2 : 1;
+        if (Bp < span_bot) {                                 // next span: blocks [span_bot, span_bot + 64 * SPAN_BLOCKS) below the old one
+            span_bot = std::max<int64_t>(b_bot, Bp - 64 * (SPAN_BLOCKS - 1));
+            for (int q = 0; q < SPAN_BLOCKS; ++q) ends[q] = 0;
+            while (ie > ra) {                                // reads ending inside the span, descending; empty reads add nothing
+                const int64_t e1 = (int64_t)(off[ie] - base0) - 1;
+                if (e1 < span_bot) break;
+                if (off[ie] != off[ie - 1]) ends[(e1 - span_bot) >> 6] |= 1ull << (uint64_t)((e1 - span_bot) & 63);
+                --ie;
+            }
+        }
         __m512i v[2] = {ff, ff};
 #pragma GCC unroll 2
         for (int u = 0; u < 2; ++u) {
             if (u >= nb) break;
             const int64_t B = Bp - 64 * u;
-            uint64_t last = 0;
-            while (ie > ra) {                              // read ends inside the block (descending cursor)
-                const int64_t e = (int64_t)(off[ie] - base0);
-                if (e == (int64_t)(off[ie - 1] - base0)) { --ie; continue; }   // empty read
-                if (e - 1 < B) break;
-                last |= 1ull << (uint64_t)(e - 1 - B);
-                --ie;
-            }
+            const uint64_t last = ends[(B - span_bot) >> 6];
             const __mmask64 mism = ~bits64_at(match, n_words, B);
             v[u] = _mm512_mask_blend_epi8(mism, _mm512_mask_blend_epi8(last, ff, idx1), idx);
         }
