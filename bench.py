@@ -548,7 +548,7 @@ def main():
 
     # warm-up: the staging allocation, then one large call per mode (host / device packing x dense / compact transport):
     # the library measures each once and keeps the fastest (query.cu, tasks.h: choose_mode)
-    for _ in range(max(8, a.warmup)):   # first call allocates the staging; six (packing x transport) modes are each tried once
+    for _ in range(max(10, a.warmup)):   # first call allocates the staging; eight (packing x transport) modes are each tried once
         e2e_dense()
     sampler.active.set()
     e2e_s = timed(e2e_dense, world)

@@ -266,8 +266,9 @@ class ColPml:
     @property
     def last_transport(self) -> str:
         """How the dense results of the last query() crossed the link: "dense", "compact" (expanded on the host) or
-        "pml-dense+cid-compact" (PML copied as it is, only the sparse chain ids in compact form)."""
-        return {0: "dense", 1: "compact", 2: "pml-dense+cid-compact"}.get(_L.colbwt_index_last_transport(self._h), "?")
+        "pml-dense+cid-compact" (PML copied as it is, only the sparse chain ids in compact form) or "mixed" (chunks alternate
+        between "dense" and "compact": the copy engine and the host threads fill the arrays together)."""
+        return {0: "dense", 1: "compact", 2: "pml-dense+cid-compact", 3: "mixed"}.get(_L.colbwt_index_last_transport(self._h), "?")
 
     @property
     def last_bytes(self) -> tuple:

@@ -532,7 +532,9 @@ enum OutKind {
     OUT_DENSE = 0,              // dense PML + CID arrays, copied as they are (2-5 bytes per base over PCIe)
     OUT_DENSE_VIA_COMPACT = 1,  // dense arrays for the caller, but the link carries the compact form and the host threads expand it
     OUT_COMPACT = 2,            // colbwt_query_compact: the compact form is the result
-    OUT_DENSE_CID_COMPACT = 3   // dense arrays for the caller: PML copied as it is, chain ids (sparse) cross the link in compact form
+    OUT_DENSE_CID_COMPACT = 3,  // dense arrays for the caller: PML copied as it is, chain ids (sparse) cross the link in compact form
+    OUT_DENSE_MIXED = 4         // dense arrays for the caller: chunks alternate between OUT_DENSE and OUT_DENSE_VIA_COMPACT, so that the
+                                // copy engine and the host threads both write results (each chunk runs as one of those two kinds)
 };
 
 struct Slot {
@@ -554,6 +556,7 @@ struct Slot {
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};   // COLBWT_TRACE=2: H2D start / kernel start / D2H start / end
     // the chunk in flight
     bool pending = false;
+    OutKind kind = OUT_DENSE;   // how THIS chunk's results travel (the call's kind, or one of the two kinds a mixed call alternates)
     int phase = 0;              // compact forms: 1 = fixed part on its way, values not yet requested; 2 = everything enqueued
     size_t chunk = 0;           // index into the job's chunk list
     uint64_t out_base = 0, out_bases = 0, n_values = 0, values_off = 0;
@@ -800,7 +803,7 @@ static int drain(QueryJob &J, Slot &k, QueryJob::DevTimes &tm)
     t0 = now_s();
     const Chunk &c = J.chunks[k.chunk];
     Pool &pool = Pool::get();
-    if (J.kind == OUT_DENSE) {
+    if (k.kind == OUT_DENSE) {
         if (J.staged_out) {   // pageable destination: copy out with all packing threads (first-touch page faults included)
             uint8_t *dst[2] = {J.pml + k.out_base * (uint64_t)J.pml_width, J.cid + k.out_base};
             const uint8_t *src[2] = {k.h_out, k.h_out + J.pl->cap_bases * (uint64_t)J.pml_width + 32};
@@ -814,7 +817,7 @@ static int drain(QueryJob &J, Slot &k, QueryJob::DevTimes &tm)
         }
     } else if (k.out_bases) {
         const CompactLayout lay(k.out_bases);
-        if (J.kind == OUT_DENSE_CID_COMPACT) {
+        if (k.kind == OUT_DENSE_CID_COMPACT) {
             // PML has landed in the caller's array by DMA; the chain ids are rebuilt group by group (2048 bases each)
             const uint8_t *fx = k.h_out, *vals = k.h_out + J.pl->compact_fixed_cap;
             const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, lay.n_groups / 16));
@@ -822,7 +825,7 @@ static int drain(QueryJob &J, Slot &k, QueryJob::DevTimes &tm)
                 expand_cid_groups(reinterpret_cast<const uint32_t *>(fx + lay.cid_off), reinterpret_cast<const uint32_t *>(fx + lay.prefix_off), vals, k.out_bases,
                                   lay.n_groups * (uint64_t)t / (uint64_t)T, lay.n_groups * (uint64_t)(t + 1) / (uint64_t)T, J.cid + k.out_base);
             });
-        } else if (J.kind == OUT_DENSE_VIA_COMPACT) {
+        } else if (k.kind == OUT_DENSE_VIA_COMPACT) {
             const uint8_t *fx = k.h_out, *vals = k.h_out + J.pl->compact_fixed_cap;
             const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool.size() * 4, k.out_bases >> 16));
             const std::vector<uint64_t> cut = slice_reads(J.off, c.r0, c.r1, T);
@@ -899,7 +902,11 @@ static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTi
     k.n_values = 0;
     k.values_off = 0;
     k.phase = 2;
-    if (J.kind == OUT_DENSE) {
+    // a mixed call sends every other chunk as it is (the copy engine writes it) and the others in compact form (the host
+    // threads write them): both ways of filling the caller's arrays work at the same time
+    const OutKind kind = J.kind == OUT_DENSE_MIXED ? ((ci & 1) ? OUT_DENSE : OUT_DENSE_VIA_COMPACT) : J.kind;
+    k.kind = kind;
+    if (kind == OUT_DENSE) {
         if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[2], k.stream));
         if (J.staged_out) {
             CB_CUDA(cudaMemcpyAsync(k.h_out, k.d_pml, st.n_bases * (uint64_t)J.pml_width, cudaMemcpyDeviceToHost, k.stream));
@@ -911,7 +918,7 @@ static int enqueue_chunk(QueryJob &J, int d, Slot &k, size_t ci, QueryJob::DevTi
         J.d2h_bytes += st.n_bases * (uint64_t)(J.pml_width + 1);
         if (J.trace >= 2) CB_CUDA(cudaEventRecord(k.tev[3], k.stream));
         CB_CUDA(cudaEventRecord(k.done, k.stream));
-    } else if (st.n_bases && J.kind == OUT_DENSE_CID_COMPACT) {
+    } else if (st.n_bases && kind == OUT_DENSE_CID_COMPACT) {
         // PML goes out dense (the copy engine writes it where the caller wants it); of the chain ids only the non-zero ones
         // cross the link (bit words + per-group prefix now, the values once their number is known: finish_values)
         const CompactLayout lay(st.n_bases);
@@ -1023,12 +1030,13 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     const bool large_call = total_bases >= (64ull << 20);
     // mode = packing bit + 2 x transport; transport 0 = dense copies, 1 = compact form expanded by the host threads,
     // 2 = PML dense + chain ids compact (needs pinned result arrays: the copy engine writes the PML in place)
-    constexpr int N_MODES = 6;
+    // 3 = chunks alternate between transports 0 and 1 (copy engine and host threads fill the arrays together; pinned arrays)
+    constexpr int N_MODES = 8;
     uint32_t allowed = 0;
     for (int m = 0; m < N_MODES; ++m) {
         if ((m & 1) && !can_device_pack) continue;
         if ((m >> 1) && compact_api) continue;
-        if ((m >> 1) == 2 && pageable_out) continue;
+        if ((m >> 1) >= 2 && pageable_out) continue;
         allowed |= 1u << m;
     }
     auto pin_field = [&](const char *name, bool packing) {
@@ -1050,7 +1058,8 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
     int rule = (Pool::get().size() < 8) ? 3 : 0;
     const int mode = choose_mode(rule, allowed, rates, N_MODES, large_call);   // tasks.h
     const bool device_pack = (mode & 1) != 0;
-    const OutKind kind = compact_api ? OUT_COMPACT : ((mode >> 1) == 1 ? OUT_DENSE_VIA_COMPACT : (mode >> 1) == 2 ? OUT_DENSE_CID_COMPACT : OUT_DENSE);
+    const OutKind kind = compact_api ? OUT_COMPACT
+                         : ((mode >> 1) == 1 ? OUT_DENSE_VIA_COMPACT : (mode >> 1) == 2 ? OUT_DENSE_CID_COMPACT : (mode >> 1) == 3 ? OUT_DENSE_MIXED : OUT_DENSE);
     idx->last_packing = device_pack ? 1 : 0;
     idx->last_transport = compact_api ? 1 : (mode >> 1);
 
@@ -1164,7 +1173,8 @@ static int query_impl(colbwt_index *idx, const uint8_t *seqs, const uint64_t *of
         fprintf(stderr, "[colbwt_query] %zu chunks, %.1f Mbases, total %.1f ms = %.2f Gbases/s (%s, packing on the %s, %d host threads)\n", J.chunks.size(),
                 total_bases / 1e6, t_total * 1e3, total_bases / t_total / 1e9,
                 kind == OUT_DENSE ? (staged_out ? "dense via staging" : "dense into pinned buffers") : kind == OUT_COMPACT ? "compact result"
-                : kind == OUT_DENSE_CID_COMPACT ? "dense, PML copied + chain ids compact" : "dense, compact transport",
+                : kind == OUT_DENSE_CID_COMPACT ? "dense, PML copied + chain ids compact"
+                : kind == OUT_DENSE_MIXED ? "dense, chunks alternate between copies and compact transport" : "dense, compact transport",
                 device_pack ? "device" : "host", Pool::get().size());
     }
     if (large_call && !fresh_pipeline) rates[mode] = (double)total_bases / std::max(1e-9, t_total);

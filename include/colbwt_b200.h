@@ -156,7 +156,8 @@ int colbwt_compact_expand(const void *result, const uint64_t *off, uint64_t n_re
 int colbwt_index_last_packing(const colbwt_index *idx);
 /* How the dense results of the last colbwt_query crossed the link: 0 as they are, 1 in the compact form above, expanded
  * into the caller's arrays by the library's host threads, 2 PML copied as it is and only the chain ids (sparse) in compact
- * form (needs pinned result arrays).  Measured the same way as the packing; COLBWT_COMPACT_D2H=0|1|2 pins it. */
+ * form, 3 chunks alternating between 0 and 1 so that the copy engine and the host threads fill the arrays together (2 and 3
+ * need pinned result arrays).  Measured the same way as the packing; COLBWT_COMPACT_D2H=0|1|2|3 pins it. */
 int colbwt_index_last_transport(const colbwt_index *idx);
 /* Bytes the last colbwt_query / colbwt_query_compact on this index asked the copy engines to move, host to device and
  * device to host (diagnostic; what bench.py reports as h2d/d2h bytes per step). */

@@ -662,7 +662,38 @@ def test_dense_query_with_compact_chain_ids(cb, small_index, monkeypatch, device
         assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
 
 
-@pytest.mark.parametrize("compact", ["0", "1", "2"])
+@pytest.mark.parametrize("device_pack", ["0", "1"])
+def test_dense_query_with_alternating_transports(cb, small_index, monkeypatch, device_pack):
+    """COLBWT_COMPACT_D2H=3: chunks alternate between plain copies and the compact form expanded by the host threads, so
+    that the copy engine and the host cores fill the caller's (pinned) arrays together; many small chunks here."""
+    monkeypatch.setenv("COLBWT_COMPACT_D2H", "3")
+    monkeypatch.setenv("COLBWT_DEVICE_PACK", device_pack)
+    monkeypatch.setenv("COLBWT_CHUNK_BASES", "40000")
+    orc = oracle.Oracle(small_index["path"])
+    tbl = cb.ColPml.load(small_index["path"])
+    for seqs, off in _compact_cases(small_index):
+        want_p, want_c = orc.query_batch(seqs, off)
+        h_seqs = cb.PinnedArray(seqs.size, np.uint8)
+        h_seqs.array[:] = seqs
+        widths = (cb.PML_U8, cb.PML_U16, cb.PML_U32) if int(np.diff(off).max()) < 256 else (cb.PML_U16, cb.PML_U32)
+        for width in widths:
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width]
+            pp, pc = cb.PinnedArray(seqs.size, dt), cb.PinnedArray(seqs.size, np.uint8)
+            pp.array[:] = 0xAB
+            pc.array[:] = 0xEE
+            for _ in range(2):                                            # second call: every slot has served both kinds of chunk
+                tbl.query(h_seqs.array, off, width, out=(pp.array, pc.array))
+                assert tbl.last_transport == "mixed"
+                assert np.array_equal(pp.array.astype(np.uint32), want_p) and np.array_equal(pc.array, want_c)
+            h2d, d2h = tbl.last_bytes
+            if seqs.size > 200000:                                        # several chunks: some went dense, some compact
+                assert seqs.size * 0.2 * (width + 1) < d2h < seqs.size * 0.9 * (width + 1)
+        pml, cid = tbl.query(seqs, off, cb.PML_U16)                      # pageable results: another transport serves them
+        assert tbl.last_transport != "mixed"
+        assert np.array_equal(pml.astype(np.uint32), want_p) and np.array_equal(cid, want_c)
+
+
+@pytest.mark.parametrize("compact", ["0", "1", "2", "3"])
 def test_two_replicas_on_one_gpu_feeder_threads(cb, small_index, monkeypatch, compact):
     """Two replicas of the table on the SAME device: exercises the per-device feeder threads of colbwt_query (one per
     replica, chunks taken from a shared counter) on a single-GPU box; results must land in input order."""
