@@ -12,8 +12,13 @@ no data-path collective).  Prints ONE JSON line (rank 0).
 
 Keys beyond the driver contract:
   value     whole-job bases/s with reads + table resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       same metric through the C-ABI call colbwt_query with HOST (pinned) buffers: host 2-bit packing, H2D, traversal,
-            D2H of PML (u8 for reads < 256 bases, else u16/u32) + CID (u8) all inside the timed region
+  e2e       same metric through the C-ABI call colbwt_query with HOST (pinned) buffers in and DENSE arrays out: read packing
+            (host or device), H2D, traversal, and the results' way back (plain copies, the compact form expanded by the host
+            threads, or both alternating: the library measures and says which in `packing` / `transport`) all inside the timed
+            region; byte counts from the library (colbwt_index_last_bytes).  Under torchrun also `alone_value` (rank 0 running
+            the same call while the others idle) and `efficiency_vs_alone`
+  e2e_compact  the same reads through colbwt_query_compact (match bit per base + non-zero chain ids: what a consumer that
+            needs no dense arrays takes), expanded once on the host after the timed region for the parity check
   roofline  the traversal kernel against the measured HBM stream peak (MEASURED_PEAKS.json), algorithmic bytes =
             35.25 B/base (32 B gathered sector + 0.25 B read in + 3 B written); `gather` adds the
             measured random-32-B-sector rate over a buffer of the index's size and the fraction of it achieved
